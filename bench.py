@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- mel-frames/sec of the batched non-AR STYLER forward on N B200s (driver contract in the task brief).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32]
+  torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, NCCL)
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): per GPU a batch of 64 utterances,
+128 phonemes -> 1024 mel frames (teacher-forced 8 frames/phoneme), Tr = 1024 reference frames, 80-bin mels, full
+STYLER forward (style encoders, variance adaptor, LengthRegulator, clean + noisy decode, PostNet), bf16 compute.
+A "step" = one forward over one resident batch; mel-frames/s = sum(mel_len) / time.  Weak scaling: 64 utterances per
+rank; the step includes the NCCL gather of the four mel tensors to rank 0.
+
+`value`  : device-timed (CUDA events, max over ranks), inputs already resident in HBM, rotating over 4 distinct
+           batches so a step's inputs are never L2-resident from their previous use (4 x 46 MB > 126 MB L2; the
+           per-step activation traffic is itself >> L2).
+`e2e`    : same metric through the public API (styler_b200.STYLER.forward) with HOST (pinned) inputs: H2D of the
+           step's inputs and D2H of the post-net mels + lengths inside the timed region.
+`roofline`: dominant kernel = FFN Conv1d k=9 256->1024 implicit GEMM (conv1d_tc), CUDA events around each of its
+           launches inside the timed steps; FLOPs/launch = 2*B*T*1024*9*256.
+`cpu_baseline`: the oracle port (torch CPU fp32, all host threads) on a bounded sample (B=8 of the same workload).
+`--impl reference`: times that CPU path alone (the reference is pure PyTorch; it cannot travel to the GPU box, so the
+           oracle restatement -- pinned against the reference in tests/golden -- stands in, kind "port").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, L, T, FRAMES = 64, 128, 1024, 8
+CPU_SAMPLE_B = 8
+NBUF = 4
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tensor=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured")
+    except Exception:
+        return dict(tensor=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), start=3):
+            if any(len(r) > i and r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_forward_fps(sample_b, reps):
+    """Oracle port on the host cores: mel-frames/s of the same workload at a bounded batch."""
+    from oracle import styler_oracle as so
+    from oracle import make_golden as mg
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = so.make_state_dict(0)
+    batch = so.make_inputs(B=sample_b, L=L, seed=1234, d_mode="const", frames=FRAMES)
+    args, kw = mg.call_kwargs(batch)
+    best = None
+    with torch.no_grad():
+        so.styler_forward(sd, *args, **kw)          # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            so.styler_forward(sd, *args, **kw)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return sample_b * T / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    from oracle import styler_oracle as so
+    from oracle import make_golden as mg
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = so.make_state_dict(0)
+    batch = so.make_inputs(B=CPU_SAMPLE_B, L=L, seed=1234, d_mode="const", frames=FRAMES)
+    a, kw = mg.call_kwargs(batch)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            so.styler_forward(sd, *a, **kw)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            so.styler_forward(sd, *a, **kw)
+        dt = time.perf_counter() - t0
+    fps = args.steps * CPU_SAMPLE_B * T / dt
+    cores = os.cpu_count() or 1
+    sample = "B=%d utterances per step of the same workload (L=%d, T=%d, teacher-forced), fp32, %d threads" % (
+        CPU_SAMPLE_B, L, T, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "mel-frames/sec (batched non-AR forward)", "value": fps, "unit": "mel-frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2] full STYLER forward, L=128 -> T=1024, 80-bin; CPU sample of B=%d" % CPU_SAMPLE_B},
+        "cpu_baseline": {"value": fps, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    from styler_b200 import dist as sdist
+    rank, world, local = sdist.init_from_env("gloo" if args.impl == "reference" else None)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from oracle import styler_oracle as so        # seeded synthetic weights/inputs only (generators, not compute)
+    from styler_b200 import STYLER, _lib
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    model = STYLER(precision=args.precision)
+    model.load_state_dict(so.make_state_dict(0))
+    model = model.to(dev).eval()
+
+    keys = ("src_seq", "mel_target", "mel_aug", "p_norm", "e_input", "src_len", "mel_len", "d_target", "p_target",
+            "e_target", "speaker_embed")
+    host, resident = [], []
+    for i in range(NBUF):
+        b = so.make_inputs(B=B_PER_GPU, L=L, seed=1234 + 16 * rank + i, d_mode="const", frames=FRAMES)
+        host.append({k: b[k].pin_memory() for k in keys})
+        resident.append({k: b[k].to(dev) for k in keys})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    frames_per_step = int(host[0]["mel_len"].sum().item())
+
+    def step(bt):
+        out = model(bt["src_seq"], bt["mel_target"], bt["mel_aug"], bt["p_norm"], bt["e_input"], bt["src_len"],
+                    bt["mel_len"], d_target=bt["d_target"], p_target=bt["p_target"], e_target=bt["e_target"],
+                    max_src_len=L, max_mel_len=T, speaker_embed=bt["speaker_embed"])
+        if world > 1:
+            sdist.gather_to_rank0([out[0][0], out[0][1], out[1][0], out[1][1], out[7]])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / 1e3, wall
+
+    for i in range(args.warmup):
+        step(resident[i % NBUF])
+    torch.cuda.synchronize()
+
+    # ---- device-resident timed region (value) + per-launch events on the dominant kernel ----------------------
+    eng = model._engine_for()
+    eng.prof = []
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clocks:
+        secs, wall = timed(lambda i: step(resident[i % NBUF]), args.steps)
+    launches = _lib.launch_count() - launches0
+    prof, eng.prof = eng.prof, None
+    torch.cuda.synchronize()
+    value = world * frames_per_step * args.steps / secs
+
+    dec = [(e0.elapsed_time(e1), b, t) for (e0, e1, b, t) in prof if t == T]      # decoder-level launches only
+    peaks = load_peaks()
+    roof = None
+    if dec:
+        avg_ms = sum(d[0] for d in dec) / len(dec)
+        flops = 2.0 * dec[0][1] * dec[0][2] * 1024 * 9 * 256
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "dominant_kernel.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "conv1d_tc_kernel<bf16> FFN Conv1d k=9 256->1024 (+bias+ReLU)",
+                "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
+                "peak_source": peaks["src"] + " bf16_tflops_sustained", "avg_launch_ms": avg_ms, "launches_timed": len(dec),
+                "flops_per_launch": flops, "traffic": traffic}
+
+    # ---- end to end through the public API with host buffers ---------------------------------------------------
+    d2h_bufs = [torch.empty(B_PER_GPU, T, 80, dtype=torch.float32).pin_memory() for _ in range(2)]
+    len_buf = torch.empty(B_PER_GPU, dtype=torch.int64).pin_memory()
+
+    def e2e_step(i):
+        hb = host[i % NBUF]
+        bt = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        out = step(bt)
+        d2h_bufs[0].copy_(out[1][0], non_blocking=True)
+        d2h_bufs[1].copy_(out[1][1], non_blocking=True)
+        len_buf.copy_(out[7], non_blocking=True)
+
+    e2e_step(0)
+    e2e_secs, e2e_wall = timed(e2e_step, args.steps)
+    e2e_secs = max(e2e_secs, e2e_wall if world == 1 else e2e_secs)
+    e2e_value = world * frames_per_step * args.steps / e2e_secs
+    d2h_bytes = 2 * d2h_bufs[0].numel() * 4 + len_buf.numel() * 8
+
+    if rank != 0:
+        return
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        fps, best = cpu_forward_fps(CPU_SAMPLE_B, 3)
+        cpu = {"value": fps, "unit": "mel-frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "oracle port (torch CPU fp32, position table cached), B=%d utterances of the same workload, "
+                         "best of 3 (%.2f s each)" % (CPU_SAMPLE_B, best)}
+    print(json.dumps({
+        "metric": "mel-frames/sec (batched non-AR forward)", "value": value, "unit": "mel-frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: full STYLER forward, B=%d/GPU, phoneme_len=%d -> mel_len=%d "
+                               "(teacher-forced %d frames/phoneme), ref mel %d frames, 80-bin, %s compute; random-init weights"
+                               % (B_PER_GPU, L, T, FRAMES, T, args.precision),
+                   "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world,
+                   "l2": "inputs rotate over %d resident batches (> L2); per-step activations >> L2; no explicit flush" % NBUF},
+        "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_secs / args.steps},
+        "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
+        "wall_s_timed_region": wall}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/* styler_b200 -- C ABI of the B200-native STYLER hot path (libstyler_b200.so).
+ *
+ * The reference (keonlee9420/STYLER) is pure Python/PyTorch and has no FFI layer; its boundary for this
+ * path is the nn.Module API (styler.py:13-58, audio/stft.py:120-160).  This header is the native boundary
+ * the Python host mirror (the styler_b200 package) binds with ctypes; each entry point names the reference code it
+ * replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates); the library never allocates
+ *     or frees device memory and keeps no state between calls except a cache of TMA descriptors;
+ *   - activations are channel-last [B][T][C]; element (b,t,c) lives at base + b*bstride + t*ld + c (ELEMENTS);
+ *   - `dtype` is the activation/weight storage type: STYLER_F32 (tcgen05 kind::tf32 or fp32 SIMT) or
+ *     STYLER_BF16 (tcgen05 kind::f16); accumulation, LayerNorm, softmax, LSTM state are always fp32;
+ *   - lengths are int64 (as the reference's src_len/mel_len), masks are derived from lengths;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *   - return 0 on success, negative = invalid argument, positive = CUDA error code; message via
+ *     styler_last_error() (thread-local).  No C++ exception crosses the ABI.
+ */
+#ifndef STYLER_B200_H_
+#define STYLER_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STYLER_F32 0
+#define STYLER_BF16 1
+
+#define STYLER_IMPL_AUTO 0
+#define STYLER_IMPL_SIMT 1   /* fp32 CUDA-core kernels (exact-fp32 parity mode, odd shapes) */
+#define STYLER_IMPL_TC 2     /* tcgen05 + TMA kernels */
+
+#define STYLER_ACT_NONE 0
+#define STYLER_ACT_RELU 1
+#define STYLER_ACT_TANH 2
+
+int styler_version(void);
+const char* styler_last_error(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t styler_launch_count(void);
+
+/* ---- Conv1d / Linear over channel-last activations with fused epilogue ----------------------------------
+ * y[b,t,n] = act2( LN( act( sum_{tap,c} x[b,t+tap-pad,c] * w[tap][n][c] + bias[n] ) + residual[b,t,n] ) )
+ * then rows t >= lens[b] are zeroed (if lens), then optional row-dot.  Replaces nn.Linear / nn.Conv1d (+ReLU /
+ * tanh / folded BatchNorm / residual + LayerNorm + masked_fill) at: transformer/SubLayers.py:41-43,58-59,72-76,
+ * 84-87; Layers.py:29,32,121-130; modules.py:30-36,103-160,211-216,250-271,438-465,502-507; styler.py:31.
+ * Time-edge taps read zeros (Conv1d zero padding); tiles never cross utterances. */
+typedef struct {
+  const void* x; int64_t x_bstride; int32_t x_ld;       /* input  [B][T][Cin], dtype */
+  int32_t B, T, Cin;
+  const void* w;                                         /* packed weights [KS][N][Cin], dtype */
+  int32_t N, KS, pad;
+  const float* bias;                                     /* [N] fp32 or NULL */
+  int32_t act;                                           /* STYLER_ACT_* applied before residual/LN */
+  const void* residual; int64_t r_bstride; int32_t r_ld; /* dtype, or NULL; r_ld==0 broadcasts one row over t */
+  int32_t residual_is_f32;                               /* 1: `residual` is fp32 whatever `dtype` is */
+  const float* ln_gamma; const float* ln_beta; float ln_eps; /* LayerNorm over the N outputs if ln_gamma != NULL */
+  int32_t act2;                                          /* STYLER_ACT_* applied after LN */
+  const int64_t* lens;                                   /* [B] or NULL */
+  const float* dot_w; float dot_b; float* dot_out;       /* optional: dot_out[b*T+t] = <y[b,t,:],dot_w>+dot_b (0 if masked) */
+  void* out; int64_t o_bstride; int32_t o_ld;            /* dtype output or NULL */
+  float* out_f32; int64_t of_bstride; int32_t of_ld;     /* optional fp32 copy of the output or NULL */
+  void* vt; int32_t vt_col0; int64_t vt_bstride; int32_t vt_ld; /* optional: columns n >= vt_col0 are stored
+                                                            transposed, vt[b][n-vt_col0][t] (dtype), instead of `out` */
+  int32_t dtype;                                         /* STYLER_F32 | STYLER_BF16 */
+  int32_t impl;                                          /* STYLER_IMPL_* */
+} styler_conv1d_args;
+int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream);
+
+/* ---- Scaled-dot-product multi-head self-attention (transformer/Modules.py:14-25, SubLayers.py:44-56) ----
+ * qk: [B][T][2*H*64] (Q columns then K columns, head h at h*64; 1/temperature already folded into Q),
+ * vt: [B][H*64][vt_ld] (V transposed), ctx: [B][T][H*64].  Keys >= lens[b] are masked (-inf); padded query
+ * rows are computed like the reference.  The attention matrix is never written. */
+int styler_attention_fwd(const void* qk, int64_t qk_bstride, int32_t qk_ld, const void* vt, int64_t vt_bstride,
+                         int32_t vt_ld, const int64_t* lens, void* ctx, int64_t ctx_bstride, int32_t ctx_ld,
+                         int32_t B, int32_t T, int32_t H, int32_t dtype, int32_t impl, void* stream);
+
+/* ---- Embedding + sinusoid position (transformer/Models.py:52-55,73-74) and position add (:124-125) ---- */
+int styler_embed_pos_fwd(const int64_t* src_seq, const float* emb, int32_t vocab, const float* pos, void* out,
+                         int32_t B, int32_t L, int32_t D, int32_t dtype, void* stream);
+/* out[b,t,:] = (a ? a[b,t,:] : 0) + (rowvec ? rowvec[b,:] : 0) + (pos ? pos[t,:] : 0) + (a2 ? a2[b,t,:] : 0)   (dtype io) */
+int styler_add_fwd(const void* a, int64_t a_bstride, int32_t a_ld, const void* a2, int64_t a2_bstride,
+                   int32_t a2_ld, const void* rowvec, int32_t rowvec_ld, const float* pos, void* out,
+                   int64_t o_bstride, int32_t o_ld, int32_t B, int32_t T, int32_t C, int32_t dtype, void* stream);
+int styler_cast_fwd(const float* x, void* out, int64_t n, int32_t dtype, void* stream);
+
+/* ---- quantize_1D_torch index (utils.py:417-429): 0 if x<=0 else rint(x*255)+1; bit-exact integers ---- */
+int styler_quantize_index_fwd(const float* x, int32_t* idx, int64_t n, void* stream);
+/* First audio-encoder conv on a 257-way one-hot input (modules.py:218-223 + :119-146) as a 5-tap weight gather:
+ * out[b,t,c] = bias[c] + sum_tap wg[tap][idx[b,t+tap-2]][c]   (out-of-range taps contribute 0) */
+int styler_onehot_conv_fwd(const int32_t* idx, const float* wg, const float* bias, void* out, int32_t B, int32_t T,
+                           int32_t C, int32_t nidx, int32_t KS, int32_t dtype, void* stream);
+
+/* ---- GroupNorm(C/16 groups) over (16 channels x ALL T incl. padding) + ReLU, in place (modules.py:113,168-172) */
+int styler_groupnorm_relu_fwd(void* x, int64_t bstride, int32_t ld, const float* gamma, const float* beta,
+                              float* stats_ws /* [B*C/16*2] */, int32_t B, int32_t T, int32_t C, int32_t ch_per_group,
+                              float eps, int32_t dtype, void* stream);
+
+/* ---- Mel Calibrator (utils.py:351-384): per utterance resample mel_len[b] frames to src_len[b] rows by
+ * segment mean (sizes q+1 for the first r segments, q after) or repeat; rows >= src_len[b] are zero. */
+int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const int64_t* mel_len,
+                              const int64_t* src_len, void* out, int64_t o_bstride, int32_t o_ld, int32_t B,
+                              int32_t Tr, int32_t L, int32_t C, int32_t dtype, void* stream);
+
+/* ---- One layer of a bidirectional LSTM over the padded grid (modules.py:179-182; nn.LSTM, gates i,f,g,o).
+ * gx: fp32 [B][L][8H] = x @ [W_ih_fwd ; W_ih_rev]^T + (b_ih+b_hh) (produced by styler_conv1d_fwd);
+ * whh: fp32 [2][4H][H]; out: [B][L][2H] (fwd | rev), dtype. */
+int styler_bilstm_layer_fwd(const float* gx, const float* whh, void* out, int64_t o_bstride, int32_t o_ld,
+                            int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
+
+/* ---- AugmentationClassifier tail (modules.py:34-45): Linear(256->2) + LogSoftmax + mean over L ---- */
+int styler_classifier_tail_fwd(const void* h, int64_t h_bstride, int32_t h_ld, const float* w /*[2][C]*/,
+                               const float* b /*[2]*/, float* out /*[B][2]*/, int32_t B, int32_t L, int32_t C,
+                               int32_t dtype, void* stream);
+
+/* ---- Duration rounding (modules.py:357-358): clamp(rint(exp(log_d) - offset) * d_control, min 0) ---- */
+int styler_duration_round_fwd(const float* log_d, float* dur, int64_t n, float log_offset, float d_control,
+                              void* stream);
+/* ---- LengthRegulator (modules.py:396-423, utils.py:332-348): integer scan + gather-expand.
+ * dur_i64 (teacher) or dur_f32 (rounded prediction; truncated toward zero like int(x.item())).
+ * mel_len[b] = un-cropped total; out rows >= min(mel_len[b], Tmax) are zero.  Integers are bit-exact.
+ * cum_ws: int32 [B][L] workspace (inclusive scan, kept for tests). */
+int styler_length_regulator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const int64_t* dur_i64,
+                                const float* dur_f32, void* out, int64_t o_bstride, int32_t o_ld, int64_t* mel_len,
+                                int32_t* cum_ws, int32_t B, int32_t L, int32_t Tmax, int32_t C, int32_t dtype,
+                                void* stream);
+
+/* ---- bucketize + embedding + 4-way sum (modules.py:365-385):
+ * x[b,t,:] = text[b,t,:] + pitch_emb[bucket(p[b,t]*p_scale, pitch_bins)] + spk[b,t,:] + energy_emb[bucket(e*e_scale)]
+ * (same summation order as the reference); optionally also x_noisy = x + noise; bucket = #bins < value
+ * (torch.bucketize right=False); indices optionally returned (int32) for bit-exact tests.  When a scale
+ * (p_control / e_control, modules.py:370,380) differs from 1 the scaled prediction is written back in place. */
+int styler_bucket_embed_sum_fwd(const void* text, const void* spk, const void* noise, int64_t in_bstride,
+                                int32_t in_ld, float* p_val, float* e_val, float p_scale, float e_scale,
+                                const float* pitch_bins, const float* energy_bins, int32_t nbins,
+                                const float* pitch_emb, const float* energy_emb, void* out, void* out_noisy,
+                                int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx, int32_t B, int32_t T,
+                                int32_t C, int32_t dtype, void* stream);
+
+/* ---- TacotronSTFT.mel_spectrogram (audio/stft.py:51-79,141-160; audio_processing.py:80-86):
+ * reflect pad n_fft/2, periodic Hann, 1024-point real FFT per hop, magnitude, mel_basis matmul,
+ * log(clamp(.,1e-5)), energy = L2 norm over the 513 bins.  y fp32 [B][N]; mel fp32 [B][n_mels][F];
+ * energy fp32 [B][F]; F = 1 + N/hop.  mel_basis fp32 [n_mels][n_fft/2+1]. */
+int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
+                        int32_t* band_ws /* [2*n_mels] workspace: non-zero band of each filter row */, float* mel,
+                        float* energy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYLER_B200_H_ */

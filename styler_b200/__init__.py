@@ -1,0 +1,18 @@
+"""styler_b200 -- B200-native (sm_100a) implementation of the STYLER non-autoregressive mel-synthesis forward
+and the TacotronSTFT mel front end, behind the reference's Python surface.  See DESIGN.md / INTEGRATION.md."""
+from . import _lib  # noqa: F401
+
+__all__ = ["STYLER", "TacotronSTFT", "ops", "hparams"]
+
+
+def __getattr__(name):
+    if name == "STYLER":
+        from .model import STYLER
+        return STYLER
+    if name == "TacotronSTFT":
+        from .stft import TacotronSTFT
+        return TacotronSTFT
+    if name in ("ops", "hparams", "model", "stft", "engine", "dist"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError(name)

@@ -1,0 +1,108 @@
+// C-ABI plumbing: version, thread-local error string, launch counter, TMA descriptor cache.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace sb {
+
+static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- cuTensorMapEncodeTiled via the runtime's driver-entry-point lookup ------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  uint64_t v[16];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 16; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+    return static_cast<size_t>(h);
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+
+int make_tmap(CUtensorMap* out, const void* base, int elem, int rank, const uint64_t* dims, const uint64_t* strides,
+              const uint32_t* box) {
+  SB_REQUIRE(rank >= 2 && rank <= 4, "make_tmap: rank %d unsupported", rank);
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = reinterpret_cast<uint64_t>(base);
+  key.v[1] = (static_cast<uint64_t>(elem) << 8) | static_cast<uint64_t>(rank);
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[6 + i] = i + 1 < rank ? strides[i] : 0;
+    key.v[10 + i] = box[i];
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  SB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver / GPU?)");
+  const int es = elem == 1 ? 2 : 4;
+  SB_REQUIRE((reinterpret_cast<uint64_t>(base) & 15) == 0, "TMA base pointer %p not 16-byte aligned", base);
+  for (int i = 0; i + 1 < rank; ++i)
+    SB_REQUIRE(strides[i] % 16 == 0, "TMA stride[%d]=%llu bytes not a multiple of 16", i,
+               (unsigned long long)strides[i]);
+  SB_REQUIRE(box[0] * es == 128, "TMA inner box must span 128 bytes (got %u)", box[0] * es);
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], est[4];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; est[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+  CUtensorMapDataType dt = elem == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                         : elem == 0 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, est,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u)",
+             (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+             (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1]);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmaps.size() > 8192) g_tmaps.clear();
+    g_tmaps.emplace(key, *out);
+  }
+  return 0;
+}
+
+}  // namespace sb
+
+extern "C" {
+int styler_version(void) { return 100; }
+const char* styler_last_error(void) { return sb::g_err; }
+int64_t styler_launch_count(void) { return sb::g_launch_count; }
+}

@@ -1,0 +1,357 @@
+// Multi-head scaled-dot-product self-attention with key-padding mask (transformer/Modules.py:14-25,
+// SubLayers.py:44-56 of the reference), never materialising the [T,T] attention matrix.
+//
+//  * attention_tc  : flash-style on tcgen05.  One CTA per (utterance, head, 128-query tile).
+//        warp 0  TMA producer: Q tile once, then K tile [128 keys x 64] and V^T tile [64 x 128 keys] per step
+//                (double-buffered for bf16), all 128B-swizzled K-major;
+//        warp 1  MMA issuer: S = Q.K^T (128x128 fp32 in TMEM cols 0..127), then O_j = P.V (128x64, cols 128..191);
+//        warps 2-5 softmax: thread r owns query row r; two passes over S in TMEM (row max, then exp / row sum),
+//                P written to swizzled smem as the next MMA's A operand, running max/sum + O accumulated in
+//                registers (online softmax), key tiles beyond lens[b] are skipped entirely.
+//    1/temperature is folded into W_q at pack time (exact: 1/8 is a power of two).
+//  * attention_simt: fp32 warp-per-query reference implementation (exact-fp32 mode and on-device cross-check).
+//
+// Bounding roofline: tensor pipe (4*T*64 FLOP per query row per head) with an SFU (exp) co-bound.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace sb {
+namespace {
+
+// ----------------------------------------------------------------------------------------------- SIMT
+template <typename T>
+__global__ void __launch_bounds__(128) attention_simt_kernel(const T* qk, long long qk_bs, int qk_ld, const T* vt,
+                                                             long long vt_bs, int vt_ld, const int64_t* lens, T* ctx,
+                                                             long long ctx_bs, int ctx_ld, int Tlen, int H) {
+  extern __shared__ float psm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y / H, h = blockIdx.y % H;
+  const int tq = blockIdx.x * 4 + warp;
+  if (tq >= Tlen) return;
+  float* p = psm + static_cast<size_t>(warp) * Tlen;
+  int len = lens != nullptr ? static_cast<int>(lens[b]) : Tlen;
+  len = len < Tlen ? len : Tlen;
+  const int D = H * 64;
+  float q[64];
+  const T* qrow = qk + b * qk_bs + static_cast<long long>(tq) * qk_ld + h * 64;
+#pragma unroll
+  for (int d = 0; d < 64; ++d) q[d] = DT<T>::ld(qrow + d);
+  float mx = -INFINITY;
+  for (int k = lane; k < len; k += 32) {
+    const T* krow = qk + b * qk_bs + static_cast<long long>(k) * qk_ld + D + h * 64;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) s = fmaf(q[d], DT<T>::ld(krow + d), s);
+    p[k] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int k = lane; k < len; k += 32) {
+    const float e = expf(p[k] - mx);
+    p[k] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  T* orow = ctx + b * ctx_bs + static_cast<long long>(tq) * ctx_ld + h * 64;
+  for (int d = lane; d < 64; d += 32) {
+    const T* vrow = vt + b * vt_bs + static_cast<long long>(h * 64 + d) * vt_ld;
+    float acc = 0.f;
+    for (int k = 0; k < len; ++k) acc = fmaf(p[k], DT<T>::ld(vrow + k), acc);
+    DT<T>::st(orow + d, len > 0 ? acc / sum : 0.f);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- tcgen05
+constexpr int kQ = 128;    // queries per CTA
+constexpr int kKV = 128;   // keys per step
+constexpr int kThreadsTc = 192;
+
+template <typename T> struct AttnCfg {
+  static constexpr int es = sizeof(T);
+  static constexpr int bke = 128 / es;              // elements per 128-byte slice
+  static constexpr int qk_slices = 64 / bke;        // slices covering the 64-wide head dim  (bf16 1, fp32 2)
+  static constexpr int pv_slices = kKV / bke;       // slices covering 128 keys              (bf16 2, fp32 4)
+  static constexpr int q_bytes = qk_slices * kQ * 128;
+  static constexpr int k_bytes = qk_slices * kKV * 128;
+  static constexpr int v_bytes = pv_slices * 64 * 128;
+  static constexpr int p_bytes = pv_slices * kQ * 128;
+  static constexpr int kv_stages = es == 2 ? 2 : 1;
+  static constexpr int umma_k = 32 / es;
+  static constexpr size_t smem = q_bytes + kv_stages * (k_bytes + v_bytes) + p_bytes + 1024 + 256;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK,
+                                                                  const __grid_constant__ CUtensorMap tmVT,
+                                                                  const int64_t* __restrict__ lens, T* __restrict__ ctx,
+                                                                  long long ctx_bs, int ctx_ld, int Tlen, int H,
+                                                                  int q_tiles) {
+  using C = AttnCfg<T>;
+  constexpr bool kTf32 = C::es == 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + C::q_bytes;                     // per stage: K then V^T
+  uint8_t* sP = sKV + C::kv_stages * (C::k_bytes + C::v_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::p_bytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                       // [2]
+  uint64_t* kv_empty = bars + 3;                      // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % q_tiles;
+  const int h = (blockIdx.x / q_tiles) % H;
+  const int b = blockIdx.x / (q_tiles * H);
+  const int t0 = qt * kQ;
+  int len = lens != nullptr ? static_cast<int>(lens[b]) : Tlen;
+  len = len < Tlen ? len : Tlen;
+  const int nkt = (len + kKV - 1) / kKV;
+  const int D = H * 64;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmVT);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0 && nkt > 0) {
+      mbar_arrive_expect_tx(q_full, C::q_bytes);
+      for (int sl = 0; sl < C::qk_slices; ++sl)
+        tma_load_3d(sQ + sl * kQ * 128, &tmQK, q_full, h * 64 + sl * C::bke, t0, b);
+      for (int j = 0; j < nkt; ++j) {
+        const int s = j % C::kv_stages;
+        const uint32_t ph = (j / C::kv_stages) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], C::k_bytes + C::v_bytes);
+        uint8_t* sK = sKV + s * (C::k_bytes + C::v_bytes);
+        uint8_t* sV = sK + C::k_bytes;
+        for (int sl = 0; sl < C::qk_slices; ++sl)
+          tma_load_3d(sK + sl * kKV * 128, &tmQK, &kv_full[s], D + h * 64 + sl * C::bke, j * kKV, b);
+        for (int sl = 0; sl < C::pv_slices; ++sl)
+          tma_load_3d(sV + sl * 64 * 128, &tmVT, &kv_full[s], j * kKV + sl * C::bke, h * 64, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkt > 0) {
+      const uint32_t fmt = kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16;
+      const uint32_t idesc_s = umma_idesc(fmt, kQ, kKV);
+      const uint32_t idesc_o = umma_idesc(fmt, kQ, 64);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkt; ++j) {
+        const int s = j % C::kv_stages;
+        mbar_wait(&kv_full[s], (j / C::kv_stages) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ);
+        const uint32_t k_addr = smem_u32(sKV + s * (C::k_bytes + C::v_bytes));
+        const uint32_t v_addr = k_addr + C::k_bytes;
+        const uint32_t p_addr = smem_u32(sP);
+#pragma unroll
+        for (int kk = 0; kk < 64 / C::umma_k; ++kk) {
+          const int sl = (kk * 32) / 128, off = (kk * 32) % 128;
+          umma_ss<kTf32>(tmem_S, umma_desc_k_sw128(q_addr + sl * kQ * 128 + off),
+                         umma_desc_k_sw128(k_addr + sl * kKV * 128 + off), idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kKV / C::umma_k; ++kk) {
+          const int sl = (kk * 32) / 128, off = (kk * 32) % 128;
+          umma_ss<kTf32>(tmem_O, umma_desc_k_sw128(p_addr + sl * kQ * 128 + off),
+                         umma_desc_k_sw128(v_addr + sl * 64 * 128 + off), idesc_o, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int t = t0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    uint8_t* p_row = sP + r * 128;
+    const int sw = r & 7;
+    for (int j = 0; j < nkt; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * kKV;
+      float mx = m_run;
+      for (int c = 0; c < kKV; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_S + lane_off + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (kbase + c + i < len) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      const float alpha = m_run == -INFINITY ? 0.f : exp2f((m_run - mx) * kLog2e);
+      l_run *= alpha;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) o[i] *= alpha;
+      const float mxl = mx * kLog2e;
+      for (int c = 0; c < kKV; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_S + lane_off + c, raw);
+        tmem_ld_wait();
+        float pv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e = kbase + c + i < len ? exp2f(fmaf(__uint_as_float(raw[i]), kLog2e, -mxl)) : 0.f;
+          pv[i] = e;
+          l_run += e;
+        }
+        // P[r][c..c+15] -> K-major 128B-swizzled smem (A operand of the PV MMA)
+        const int byte0 = c * C::es;                       // byte offset of key c within the row
+        uint8_t* slice = p_row + (byte0 / 128) * (kQ * 128);
+        const int ch0 = (byte0 % 128) / 16;
+        if constexpr (C::es == 2) {
+          float a0[8], a1[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a0[i] = pv[i]; a1[i] = pv[8 + i]; }
+          store8(reinterpret_cast<__nv_bfloat16*>(slice + ((ch0 ^ sw) * 16)), a0);
+          store8(reinterpret_cast<__nv_bfloat16*>(slice + (((ch0 + 1) ^ sw) * 16)), a1);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(slice + (((ch0 + g) ^ sw) * 16)) =
+                make_float4(pv[4 * g], pv[4 * g + 1], pv[4 * g + 2], pv[4 * g + 3]);
+        }
+      }
+      m_run = mx;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_O + lane_off + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c + i] += __uint_as_float(raw[i]);
+      }
+    }
+    if (t < Tlen) {
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      T* orow = ctx + b * ctx_bs + static_cast<long long>(t) * ctx_ld + h * 64;
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = o[c + i] * inv;
+        store8(orow + c, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+template <typename T>
+int launch_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t vt_bs, int vt_ld,
+              const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int Tlen, int H, cudaStream_t s) {
+  using C = AttnCfg<T>;
+  const int D = H * 64;
+  CUtensorMap tmQK, tmVT;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(2 * D), static_cast<uint64_t>(Tlen), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(qk_ld) * C::es, static_cast<uint64_t>(qk_bs) * C::es};
+    const uint32_t box[3] = {static_cast<uint32_t>(C::bke), 128, 1};
+    int rc = make_tmap(&tmQK, qk, C::es == 2 ? 1 : 0, 3, dims, strides, box);
+    if (rc != 0) return rc;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(Tlen), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(vt_ld) * C::es, static_cast<uint64_t>(vt_bs) * C::es};
+    const uint32_t box[3] = {static_cast<uint32_t>(C::bke), 64, 1};
+    int rc = make_tmap(&tmVT, vt, C::es == 2 ? 1 : 0, 3, dims, strides, box);
+    if (rc != 0) return rc;
+  }
+  auto kern = attention_tc_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
+    attr_set = true;
+  }
+  const int q_tiles = ceil_div(Tlen, kQ);
+  kern<<<B * H * q_tiles, kThreadsTc, C::smem, s>>>(tmQK, tmVT, lens, static_cast<T*>(ctx), ctx_bs, ctx_ld, Tlen, H,
+                                                    q_tiles);
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+int attention_simt(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t vt_bs, int vt_ld,
+                   const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int T, int H, int dtype,
+                   cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(4) * T * sizeof(float);
+  SB_REQUIRE(smem <= 200 * 1024, "attention_simt: T=%d too long", T);
+  dim3 grid(ceil_div(T, 4), B * H);
+  SB_DISPATCH_DTYPE(dtype, TT, {
+    auto kern = attention_simt_kernel<TT>;
+    if (smem > 48 * 1024)
+      SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, 128, smem, s>>>(static_cast<const TT*>(qk), qk_bs, qk_ld, static_cast<const TT*>(vt), vt_bs, vt_ld,
+                                 lens, static_cast<TT*>(ctx), ctx_bs, ctx_ld, T, H);
+  });
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+int attention_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t vt_bs, int vt_ld,
+                 const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int T, int H, int dtype,
+                 cudaStream_t s) {
+  const int es = dtype == STYLER_BF16 ? 2 : 4;
+  SB_REQUIRE((static_cast<int64_t>(ctx_ld) * es) % 16 == 0 && (ctx_bs * es) % 16 == 0 &&
+                 (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
+             "attention_tc: ctx must be 16-byte aligned/strided");
+  if (dtype == STYLER_BF16)
+    return launch_tc<__nv_bfloat16>(qk, qk_bs, qk_ld, vt, vt_bs, vt_ld, lens, ctx, ctx_bs, ctx_ld, B, T, H, s);
+  return launch_tc<float>(qk, qk_bs, qk_ld, vt, vt_bs, vt_ld, lens, ctx, ctx_bs, ctx_ld, B, T, H, s);
+}
+
+}  // namespace sb
+
+extern "C" int styler_attention_fwd(const void* qk, int64_t qk_bstride, int32_t qk_ld, const void* vt,
+                                    int64_t vt_bstride, int32_t vt_ld, const int64_t* lens, void* ctx,
+                                    int64_t ctx_bstride, int32_t ctx_ld, int32_t B, int32_t T, int32_t H,
+                                    int32_t dtype, int32_t impl, void* stream) {
+  using namespace sb;
+  SB_REQUIRE(qk != nullptr && vt != nullptr && ctx != nullptr, "attention: null pointer");
+  SB_REQUIRE(B > 0 && T > 0 && H > 0, "attention: bad shape B=%d T=%d H=%d", B, T, H);
+  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "attention: bad dtype %d", dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == STYLER_IMPL_AUTO) impl = STYLER_IMPL_TC;
+  if (impl == STYLER_IMPL_TC)
+    return attention_tc(qk, qk_bstride, qk_ld, vt, vt_bstride, vt_ld, lens, ctx, ctx_bstride, ctx_ld, B, T, H, dtype, s);
+  SB_REQUIRE(impl == STYLER_IMPL_SIMT, "attention: bad impl %d", impl);
+  return attention_simt(qk, qk_bstride, qk_ld, vt, vt_bstride, vt_ld, lens, ctx, ctx_bstride, ctx_ld, B, T, H, dtype, s);
+}

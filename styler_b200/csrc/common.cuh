@@ -1,0 +1,122 @@
+// Shared helpers: status/error plumbing for the C ABI, dtype traits, small device utilities.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/styler_b200.h"
+
+namespace sb {
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+#define SB_REQUIRE(cond, ...)          \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::sb::set_error(__VA_ARGS__);    \
+      return -1;                       \
+    }                                  \
+  } while (0)
+
+#define SB_CUDA_OK(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ::sb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return static_cast<int>(e__);                                                        \
+    }                                                                                      \
+  } while (0)
+
+#define SB_LAUNCH_OK()                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) {                                                              \
+      ::sb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return static_cast<int>(e__);                                                        \
+    }                                                                                      \
+    ::sb::count_launch();                                                                  \
+  } while (0)
+
+// ---- dtype traits ---------------------------------------------------------------------------------------
+template <typename T> struct DT;
+template <> struct DT<float> {
+  static constexpr int code = STYLER_F32;
+  __device__ static __forceinline__ float ld(const float* p) { return *p; }
+  __device__ static __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct DT<__nv_bfloat16> {
+  static constexpr int code = STYLER_BF16;
+  __device__ static __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ static __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// 8 consecutive elements <-> 8 floats (16-byte access for bf16, 2x16 for fp32); pointers must be 16B aligned.
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == STYLER_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == STYLER_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// dispatch on the ABI dtype code
+#define SB_DISPATCH_DTYPE(code, T, ...)                          \
+  do {                                                           \
+    if ((code) == STYLER_F32) { using T = float; __VA_ARGS__; }  \
+    else if ((code) == STYLER_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { ::sb::set_error("unsupported dtype code %d", (int)(code)); return -1; } \
+  } while (0)
+
+// entry points implemented per translation unit
+int conv1d_simt(const styler_conv1d_args& a, cudaStream_t s);
+int conv1d_tc(const styler_conv1d_args& a, cudaStream_t s);
+bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why);
+int attention_simt(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t vt_bs, int vt_ld,
+                   const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int T, int H, int dtype,
+                   cudaStream_t s);
+int attention_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t vt_bs, int vt_ld,
+                 const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int T, int H, int dtype,
+                 cudaStream_t s);
+
+}  // namespace sb

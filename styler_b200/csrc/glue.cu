@@ -1,0 +1,523 @@
+// HBM-bound glue kernels of the STYLER forward: embedding+position, adds, quantise, one-hot conv gather,
+// GroupNorm+ReLU, Mel Calibrator, classifier tail, duration rounding, LengthRegulator (integer scan +
+// vectorised gather-expand), bucketize+embedding+sum.  All are coalesced, 16-byte vectorised where the
+// layout allows, fp32 math, activation I/O in the ABI dtype.  Reference lines are cited in include/styler_b200.h.
+#include "common.cuh"
+
+namespace sb {
+namespace {
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------- embed + pos
+template <typename T>
+__global__ void embed_pos_kernel(const int64_t* __restrict__ seq, const float* __restrict__ emb, int vocab,
+                                 const float* __restrict__ pos, T* __restrict__ out, int rows, int L, int D) {
+  const int per_row = D / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(rows) * per_row) return;
+  const int row = static_cast<int>(gid / per_row), c = static_cast<int>(gid % per_row) * 8;
+  const int l = row % L;
+  long long tok = seq[row];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  float e[8], p[8], v[8];
+  load8(emb + tok * D + c, e);
+  load8(pos + static_cast<long long>(l) * D + c, p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = e[i] + p[i];
+  store8(out + static_cast<long long>(row) * D + c, v);
+}
+
+// ---------------------------------------------------------------------------------------- generic add
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, long long a_bs, int a_ld, const T* __restrict__ a2, long long a2_bs,
+                           int a2_ld, const T* __restrict__ rowvec, int rv_ld, const float* __restrict__ pos,
+                           T* __restrict__ out, long long o_bs, int o_ld, int B, int Tn, int C) {
+  const int per_row = C / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(B) * Tn * per_row) return;
+  const int c = static_cast<int>(gid % per_row) * 8;
+  const long long row = gid / per_row;
+  const int t = static_cast<int>(row % Tn), b = static_cast<int>(row / Tn);
+  float v[8], w[8];
+  if (a != nullptr) {
+    load8(a + b * a_bs + static_cast<long long>(t) * a_ld + c, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  if (rowvec != nullptr) {
+    load8(rowvec + static_cast<long long>(b) * rv_ld + c, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += w[i];
+  }
+  if (pos != nullptr) {
+    load8(pos + static_cast<long long>(t) * C + c, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += w[i];
+  }
+  if (a2 != nullptr) {
+    load8(a2 + b * a2_bs + static_cast<long long>(t) * a2_ld + c, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += w[i];
+  }
+  store8(out + b * o_bs + static_cast<long long>(t) * o_ld + c, v);
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) DT<T>::st(out + i, x[i]);
+}
+
+// ---------------------------------------------------------------------------------------- quantise / one-hot conv
+__global__ void quantize_index_kernel(const float* __restrict__ x, int32_t* __restrict__ idx, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  idx[i] = v <= 0.f ? 0 : static_cast<int32_t>(rintf(__fmul_rn(v, 255.0f))) + 1;
+}
+
+template <typename T>
+__global__ void onehot_conv_kernel(const int32_t* __restrict__ idx, const float* __restrict__ wg,
+                                   const float* __restrict__ bias, T* __restrict__ out, int B, int Tn, int C, int nidx,
+                                   int KS) {
+  const int per_row = C / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(B) * Tn * per_row) return;
+  const int c = static_cast<int>(gid % per_row) * 8;
+  const long long row = gid / per_row;
+  const int t = static_cast<int>(row % Tn), b = static_cast<int>(row / Tn);
+  const int pad = (KS - 1) / 2;
+  float acc[8];
+  load8(bias + c, acc);
+  for (int tap = 0; tap < KS; ++tap) {
+    const int tt = t + tap - pad;
+    if (tt < 0 || tt >= Tn) continue;
+    int id = idx[static_cast<long long>(b) * Tn + tt];
+    id = id < 0 ? 0 : (id >= nidx ? nidx - 1 : id);
+    float w[8];
+    load8(wg + (static_cast<long long>(tap) * nidx + id) * C + c, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += w[i];
+  }
+  store8(out + row * C + c, acc);
+}
+
+// ---------------------------------------------------------------------------------------- GroupNorm + ReLU
+// stats: one CTA per (b, group); shifted sums (shift = first element) in fp32 per thread, fp64 block combine.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, long long bs, int ld, float* __restrict__ stats,
+                                                       int Tn, int groups, int cpg, float eps) {
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const T* base = x + b * bs + g * cpg;
+  const float shift = DT<T>::ld(base);
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+    const T* p = base + static_cast<long long>(t) * ld;
+    for (int c = 0; c < cpg; c += 8) {
+      float v[8];
+      load8(p + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[i] - shift; s1 += d; s2 += d * d; }
+    }
+  }
+  __shared__ double r1[8], r2[8];
+  double d1 = warp_sum(s1), d2 = warp_sum(s2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { r1[warp] = d1; r2[warp] = d2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, q = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) { a += r1[i]; q += r2[i]; }
+    const double n = static_cast<double>(Tn) * cpg;
+    const double dm = a / n;
+    double var = q / n - dm * dm;
+    var = var < 0 ? 0 : var;
+    stats[2 * blockIdx.x] = static_cast<float>(shift + dm);
+    stats[2 * blockIdx.x + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+template <typename T>
+__global__ void gn_apply_relu_kernel(T* __restrict__ x, long long bs, int ld, const float* __restrict__ stats,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, int B, int Tn,
+                                     int C, int cpg) {
+  const int per_row = C / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(B) * Tn * per_row) return;
+  const int c = static_cast<int>(gid % per_row) * 8;
+  const long long row = gid / per_row;
+  const int t = static_cast<int>(row % Tn), b = static_cast<int>(row / Tn);
+  const int g = c / cpg;
+  const float mean = stats[2 * (b * (C / cpg) + g)], rstd = stats[2 * (b * (C / cpg) + g) + 1];
+  T* p = x + b * bs + static_cast<long long>(t) * ld + c;
+  float v[8], ga[8], be[8];
+  load8(p, v);
+  load8(gamma + c, ga);
+  load8(beta + c, be);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = fmaxf((v[i] - mean) * rstd * ga[i] + be[i], 0.f);
+  store8(p, v);
+}
+
+// ---------------------------------------------------------------------------------------- Mel Calibrator
+template <typename T>
+__global__ void mel_calibrator_kernel(const T* __restrict__ x, long long x_bs, int x_ld, const int64_t* __restrict__ mel_len,
+                                      const int64_t* __restrict__ src_len, T* __restrict__ out, long long o_bs, int o_ld,
+                                      int B, int Tr, int L, int C) {
+  const int per_row = C / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(B) * L * per_row) return;
+  const int c = static_cast<int>(gid % per_row) * 8;
+  const long long row = gid / per_row;
+  const int l = static_cast<int>(row % L), b = static_cast<int>(row / L);
+  int ml = static_cast<int>(mel_len[b]), sl = static_cast<int>(src_len[b]);
+  ml = ml > Tr ? Tr : ml;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const T* xb = x + b * x_bs + c;
+  if (l < sl && ml > 0) {
+    if (ml == sl) {
+      load8(xb + static_cast<long long>(l) * x_ld, acc);
+    } else if (ml > sl) {                        // compression: mean over segment l (get_scale(ml, sl))
+      const int q = ml / sl, r = ml % sl;
+      const int start = l * q + (l < r ? l : r), size = q + (l < r ? 1 : 0);
+      for (int k = 0; k < size; ++k) {
+        float v[8];
+        load8(xb + static_cast<long long>(start + k) * x_ld, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+      const float fs = static_cast<float>(size);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = acc[i] / fs;
+    } else {                                     // expansion: frame i repeated get_scale(sl, ml)[i] times
+      const int q = sl / ml, r = sl % ml;
+      const int boundary = r * (q + 1);
+      const int i = l < boundary ? l / (q + 1) : r + (l - boundary) / q;
+      load8(xb + static_cast<long long>(i) * x_ld, acc);
+    }
+  }
+  store8(out + b * o_bs + static_cast<long long>(l) * o_ld + c, acc);
+}
+
+// ---------------------------------------------------------------------------------------- classifier tail
+template <typename T>
+__global__ void __launch_bounds__(256) classifier_tail_kernel(const T* __restrict__ h, long long h_bs, int h_ld,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              float* __restrict__ out, int L, int C) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a0 = 0.f, a1 = 0.f;
+  for (int l = warp; l < L; l += 8) {
+    const T* row = h + b * h_bs + static_cast<long long>(l) * h_ld;
+    float z0 = 0.f, z1 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = DT<T>::ld(row + c);
+      z0 = fmaf(v, w[c], z0);
+      z1 = fmaf(v, w[C + c], z1);
+    }
+    z0 = warp_sum(z0) + bias[0];
+    z1 = warp_sum(z1) + bias[1];
+    const float m = fmaxf(z0, z1);
+    const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
+    a0 += z0 - lse;
+    a1 += z1 - lse;
+  }
+  __shared__ float s0[8], s1[8];
+  if (lane == 0) { s0[warp] = a0; s1[warp] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < 8; ++i) { t0 += s0[i]; t1 += s1[i]; }
+    out[2 * b] = t0 / L;
+    out[2 * b + 1] = t1 / L;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- duration / LengthRegulator
+__global__ void duration_round_kernel(const float* __restrict__ log_d, float* __restrict__ dur, long long n, float off,
+                                      float ctl) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dur[i] = fmaxf(__fmul_rn(rintf(__fsub_rn(expf(log_d[i]), off)), ctl), 0.f);
+}
+
+// inclusive scan of int(duration) per utterance; block per utterance, L <= 4096
+__global__ void __launch_bounds__(1024) lr_scan_kernel(const int64_t* __restrict__ d64, const float* __restrict__ d32,
+                                                       int32_t* __restrict__ cum, int64_t* __restrict__ mel_len, int L) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < L; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int v = 0;
+    if (i < L) {
+      if (d64 != nullptr) {
+        const long long d = d64[static_cast<long long>(b) * L + i];
+        v = d < 0 ? 0 : (d > 1000000 ? 1000000 : static_cast<int>(d));
+      } else {
+        const float f = d32[static_cast<long long>(b) * L + i];
+        v = f > 0.f ? (f > 1.0e6f ? 1000000 : static_cast<int>(f)) : 0;   // int(x.item()): truncation
+      }
+    }
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += n; }
+    if (lane == 31) warp_tot[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += n; }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int incl = s + (warp > 0 ? warp_tot[warp - 1] : 0) + carry;
+    if (i < L) cum[static_cast<long long>(b) * L + i] = incl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mel_len[b] = carry;
+}
+
+// warp per output frame: binary search the scan, copy the source row with 16-byte accesses
+__global__ void __launch_bounds__(256) lr_expand_kernel(const uint4* __restrict__ x, long long x_bs16, int x_ld16,
+                                                        const int32_t* __restrict__ cum, uint4* __restrict__ out,
+                                                        long long o_bs16, int o_ld16, int L, int Tmax, int row16) {
+  extern __shared__ int32_t scum[];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) scum[i] = cum[static_cast<long long>(b) * L + i];
+  __syncthreads();
+  const int total = L > 0 ? scum[L - 1] : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= Tmax) return;
+  uint4* orow = out + b * o_bs16 + static_cast<long long>(t) * o_ld16;
+  if (t < total) {
+    int lo = 0, hi = L - 1;                     // first i with cum[i] > t
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (scum[mid] > t) hi = mid; else lo = mid + 1; }
+    const uint4* srow = x + b * x_bs16 + static_cast<long long>(lo) * x_ld16;
+    for (int i = lane; i < row16; i += 32) orow[i] = __ldg(srow + i);
+  } else {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < row16; i += 32) orow[i] = z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- bucketize + embed + sum
+template <typename T>
+__global__ void __launch_bounds__(256) bucket_embed_sum_kernel(
+    const T* __restrict__ text, const T* __restrict__ spk, const T* __restrict__ noise, long long in_bs, int in_ld,
+    float* __restrict__ p_val, float* __restrict__ e_val, float p_scale, float e_scale,
+    const float* __restrict__ pbins, const float* __restrict__ ebins, int nbins, const float* __restrict__ pemb,
+    const float* __restrict__ eemb, T* __restrict__ out, T* __restrict__ out_noisy, long long o_bs, int o_ld,
+    int32_t* __restrict__ p_idx, int32_t* __restrict__ e_idx, int B, int Tn, int C) {
+  extern __shared__ float sbins[];
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) { sbins[i] = pbins[i]; sbins[nbins + i] = ebins[i]; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= static_cast<long long>(B) * Tn) return;
+  const int t = static_cast<int>(row % Tn), b = static_cast<int>(row / Tn);
+  const float pv = __fmul_rn(p_val[row], p_scale), ev = __fmul_rn(e_val[row], e_scale);
+  auto lower = [&](const float* bins, float v) {   // #bins < v  == torch.bucketize(v, bins, right=False)
+    int lo = 0, hi = nbins;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (bins[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  const int pi = lower(sbins, pv), ei = lower(sbins + nbins, ev);
+  if (lane == 0) {
+    if (p_idx != nullptr) p_idx[row] = pi;
+    if (e_idx != nullptr) e_idx[row] = ei;
+    if (p_scale != 1.0f) p_val[row] = pv;
+    if (e_scale != 1.0f) e_val[row] = ev;
+  }
+  const long long in_off = b * in_bs + static_cast<long long>(t) * in_ld;
+  const long long o_off = b * o_bs + static_cast<long long>(t) * o_ld;
+  for (int c = lane * 8; c < C; c += 256) {
+    float tx[8], sp[8], pe[8], ee[8], v[8];
+    load8(text + in_off + c, tx);
+    load8(spk + in_off + c, sp);
+    load8(pemb + static_cast<long long>(pi) * C + c, pe);
+    load8(eemb + static_cast<long long>(ei) * C + c, ee);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((tx[i] + pe[i]) + sp[i]) + ee[i];
+    store8(out + o_off + c, v);
+    if (out_noisy != nullptr) {
+      float nz[8];
+      load8(noise + in_off + c, nz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += nz[i];
+      store8(out_noisy + o_off + c, v);
+    }
+  }
+}
+
+inline int blocks_for(long long n, int per) { return static_cast<int>((n + per - 1) / per); }
+
+}  // namespace
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int styler_embed_pos_fwd(const int64_t* src_seq, const float* emb, int32_t vocab, const float* pos, void* out,
+                                    int32_t B, int32_t L, int32_t D, int32_t dtype, void* stream) {
+  SB_REQUIRE(src_seq && emb && pos && out, "embed_pos: null pointer");
+  SB_REQUIRE(B > 0 && L > 0 && D % 8 == 0, "embed_pos: bad shape");
+  const long long n = static_cast<long long>(B) * L * (D / 8);
+  SB_DISPATCH_DTYPE(dtype, T, (embed_pos_kernel<T><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                                  src_seq, emb, vocab, pos, static_cast<T*>(out), B * L, L, D)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_add_fwd(const void* a, int64_t a_bstride, int32_t a_ld, const void* a2, int64_t a2_bstride,
+                              int32_t a2_ld, const void* rowvec, int32_t rowvec_ld, const float* pos, void* out,
+                              int64_t o_bstride, int32_t o_ld, int32_t B, int32_t T, int32_t C, int32_t dtype,
+                              void* stream) {
+  SB_REQUIRE(out, "add: null pointer");
+  SB_REQUIRE(B > 0 && T > 0 && C % 8 == 0 && a_ld % 8 == 0 && o_ld % 8 == 0 && a_bstride % 8 == 0 && o_bstride % 8 == 0 &&
+                 (a2 == nullptr || (a2_ld % 8 == 0 && a2_bstride % 8 == 0)) && (rowvec == nullptr || rowvec_ld % 8 == 0),
+             "add: shapes/strides must be multiples of 8 elements");
+  SB_REQUIRE((a == nullptr || al16(a)) && al16(out) && (a2 == nullptr || al16(a2)) && (rowvec == nullptr || al16(rowvec)) &&
+                 (pos == nullptr || al16(pos)), "add: pointers must be 16-byte aligned");
+  const long long n = static_cast<long long>(B) * T * (C / 8);
+  SB_DISPATCH_DTYPE(dtype, TT, (add_kernel<TT><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                                   static_cast<const TT*>(a), a_bstride, a_ld, static_cast<const TT*>(a2), a2_bstride, a2_ld,
+                                   static_cast<const TT*>(rowvec), rowvec_ld, pos, static_cast<TT*>(out), o_bstride, o_ld, B,
+                                   T, C)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_cast_fwd(const float* x, void* out, int64_t n, int32_t dtype, void* stream) {
+  SB_REQUIRE(x && out && n > 0, "cast: bad arguments");
+  SB_DISPATCH_DTYPE(dtype, T, (cast_kernel<T><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                                  x, static_cast<T*>(out), n)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_quantize_index_fwd(const float* x, int32_t* idx, int64_t n, void* stream) {
+  SB_REQUIRE(x && idx && n > 0, "quantize_index: bad arguments");
+  quantize_index_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, idx, n);
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_onehot_conv_fwd(const int32_t* idx, const float* wg, const float* bias, void* out, int32_t B,
+                                      int32_t T, int32_t C, int32_t nidx, int32_t KS, int32_t dtype, void* stream) {
+  SB_REQUIRE(idx && wg && bias && out, "onehot_conv: null pointer");
+  SB_REQUIRE(B > 0 && T > 0 && C % 8 == 0 && nidx > 0 && KS > 0, "onehot_conv: bad shape");
+  const long long n = static_cast<long long>(B) * T * (C / 8);
+  SB_DISPATCH_DTYPE(dtype, TT, (onehot_conv_kernel<TT><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                                   idx, wg, bias, static_cast<TT*>(out), B, T, C, nidx, KS)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_groupnorm_relu_fwd(void* x, int64_t bstride, int32_t ld, const float* gamma, const float* beta,
+                                         float* stats_ws, int32_t B, int32_t T, int32_t C, int32_t ch_per_group, float eps,
+                                         int32_t dtype, void* stream) {
+  SB_REQUIRE(x && gamma && beta && stats_ws, "groupnorm: null pointer");
+  SB_REQUIRE(B > 0 && T > 0 && ch_per_group % 8 == 0 && C % ch_per_group == 0 && ld % 8 == 0 && bstride % 8 == 0 && al16(x),
+             "groupnorm: bad shape/alignment");
+  const int groups = C / ch_per_group;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SB_DISPATCH_DTYPE(dtype, TT, (gn_stats_kernel<TT><<<B * groups, 256, 0, s>>>(static_cast<const TT*>(x), bstride, ld, stats_ws,
+                                                                               T, groups, ch_per_group, eps)));
+  SB_LAUNCH_OK();
+  const long long n = static_cast<long long>(B) * T * (C / 8);
+  SB_DISPATCH_DTYPE(dtype, TT, (gn_apply_relu_kernel<TT><<<blocks_for(n, 256), 256, 0, s>>>(
+                                   static_cast<TT*>(x), bstride, ld, stats_ws, gamma, beta, B, T, C, ch_per_group)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const int64_t* mel_len,
+                                         const int64_t* src_len, void* out, int64_t o_bstride, int32_t o_ld, int32_t B,
+                                         int32_t Tr, int32_t L, int32_t C, int32_t dtype, void* stream) {
+  SB_REQUIRE(x && mel_len && src_len && out, "mel_calibrator: null pointer");
+  SB_REQUIRE(B > 0 && Tr > 0 && L > 0 && C % 8 == 0 && x_ld % 8 == 0 && o_ld % 8 == 0 && x_bstride % 8 == 0 &&
+                 o_bstride % 8 == 0 && al16(x) && al16(out), "mel_calibrator: bad shape/alignment");
+  const long long n = static_cast<long long>(B) * L * (C / 8);
+  SB_DISPATCH_DTYPE(dtype, TT, (mel_calibrator_kernel<TT><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                                   static_cast<const TT*>(x), x_bstride, x_ld, mel_len, src_len, static_cast<TT*>(out),
+                                   o_bstride, o_ld, B, Tr, L, C)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_classifier_tail_fwd(const void* h, int64_t h_bstride, int32_t h_ld, const float* w, const float* b,
+                                          float* out, int32_t B, int32_t L, int32_t C, int32_t dtype, void* stream) {
+  SB_REQUIRE(h && w && b && out && B > 0 && L > 0 && C > 0, "classifier_tail: bad arguments");
+  SB_DISPATCH_DTYPE(dtype, TT, (classifier_tail_kernel<TT><<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                                   static_cast<const TT*>(h), h_bstride, h_ld, w, b, out, L, C)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_duration_round_fwd(const float* log_d, float* dur, int64_t n, float log_offset, float d_control,
+                                         void* stream) {
+  SB_REQUIRE(log_d && dur && n > 0, "duration_round: bad arguments");
+  duration_round_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(log_d, dur, n, log_offset,
+                                                                                           d_control);
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_length_regulator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const int64_t* dur_i64,
+                                           const float* dur_f32, void* out, int64_t o_bstride, int32_t o_ld,
+                                           int64_t* mel_len, int32_t* cum_ws, int32_t B, int32_t L, int32_t Tmax, int32_t C,
+                                           int32_t dtype, void* stream) {
+  SB_REQUIRE(x && out && mel_len && cum_ws, "length_regulator: null pointer");
+  SB_REQUIRE((dur_i64 != nullptr) != (dur_f32 != nullptr), "length_regulator: exactly one of dur_i64 / dur_f32");
+  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "length_regulator: bad dtype");
+  const int es = dtype == STYLER_BF16 ? 2 : 4;
+  SB_REQUIRE(B > 0 && L > 0 && L <= 8192 && Tmax >= 0 && C > 0, "length_regulator: bad shape");
+  SB_REQUIRE((C * es) % 16 == 0 && (static_cast<int64_t>(x_ld) * es) % 16 == 0 && (static_cast<int64_t>(o_ld) * es) % 16 == 0 &&
+                 (x_bstride * es) % 16 == 0 && (o_bstride * es) % 16 == 0 && al16(x) && al16(out),
+             "length_regulator: rows must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int threads = L >= 1024 ? 1024 : ((L + 31) / 32) * 32;
+  lr_scan_kernel<<<B, threads, 0, s>>>(dur_i64, dur_f32, cum_ws, mel_len, L);
+  SB_LAUNCH_OK();
+  if (Tmax > 0) {
+    dim3 grid(ceil_div(Tmax, 8), B);
+    lr_expand_kernel<<<grid, 256, L * sizeof(int32_t), s>>>(static_cast<const uint4*>(x), x_bstride * es / 16, x_ld * es / 16,
+                                                            cum_ws, static_cast<uint4*>(out), o_bstride * es / 16,
+                                                            o_ld * es / 16, L, Tmax, C * es / 16);
+    SB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" int styler_bucket_embed_sum_fwd(const void* text, const void* spk, const void* noise, int64_t in_bstride,
+                                           int32_t in_ld, float* p_val, float* e_val, float p_scale,
+                                           float e_scale, const float* pitch_bins, const float* energy_bins, int32_t nbins,
+                                           const float* pitch_emb, const float* energy_emb, void* out, void* out_noisy,
+                                           int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx, int32_t B,
+                                           int32_t T, int32_t C, int32_t dtype, void* stream) {
+  SB_REQUIRE(text && spk && p_val && e_val && pitch_bins && energy_bins && pitch_emb && energy_emb && out,
+             "bucket_embed_sum: null pointer");
+  SB_REQUIRE(out_noisy == nullptr || noise != nullptr, "bucket_embed_sum: out_noisy needs noise");
+  SB_REQUIRE(B > 0 && T > 0 && C % 8 == 0 && in_ld % 8 == 0 && o_ld % 8 == 0 && in_bstride % 8 == 0 && o_bstride % 8 == 0 &&
+                 nbins > 0 && nbins <= 4096, "bucket_embed_sum: bad shape");
+  SB_REQUIRE(al16(text) && al16(spk) && al16(out) && (noise == nullptr || al16(noise)) &&
+                 (out_noisy == nullptr || al16(out_noisy)) && al16(pitch_emb) && al16(energy_emb),
+             "bucket_embed_sum: pointers must be 16-byte aligned");
+  const long long rows = static_cast<long long>(B) * T;
+  SB_DISPATCH_DTYPE(dtype, TT,
+                    (bucket_embed_sum_kernel<TT><<<blocks_for(rows, 8), 256, 2 * nbins * sizeof(float),
+                                                   static_cast<cudaStream_t>(stream)>>>(
+                        static_cast<const TT*>(text), static_cast<const TT*>(spk), static_cast<const TT*>(noise), in_bstride,
+                        in_ld, p_val, e_val, p_scale, e_scale, pitch_bins,
+                        energy_bins, nbins, pitch_emb, energy_emb, static_cast<TT*>(out), static_cast<TT*>(out_noisy),
+                        o_bstride, o_ld, p_idx, e_idx, B, T, C)));
+  SB_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,145 @@
+// TacotronSTFT.mel_spectrogram (audio/stft.py:51-79,141-160; audio_processing.py:80-86 of the reference).
+// The reference evaluates a dense 1026x1024 DFT as a strided Conv1d (2.1 MFLOP/frame) and bounces through
+// the host; here one CTA handles 8 consecutive frames of one utterance:
+//   stage the 8*256+768 reflect-padded samples in smem once (the 4x frame overlap is served from smem),
+//   periodic-Hann window, 1024-point real FFT as a 512-point complex Stockham radix-2 FFT + split post-pass
+//   (64 threads per frame, 4 frames in flight), magnitude for the 513 bins -> smem,
+//   energy = ||mag||_2, mel = log(max(basis @ mag, 1e-5)) using the non-zero band of each filter row.
+// Bounding roofline: HBM (464,580 algorithmic bytes per 4 s utterance); the FFT stage is smem/ALU work.
+#include "common.cuh"
+
+namespace sb {
+namespace {
+
+constexpr int NFFT = 1024, HOP = 256, NBINS = 513, FPB = 8, HALF = 512;
+constexpr int NSAMP = (FPB - 1) * HOP + NFFT;
+
+__global__ void mel_band_kernel(const float* __restrict__ basis, int n_mels, int32_t* __restrict__ band) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= n_mels) return;
+  int lo = NBINS, hi = -1;
+  for (int k = lane; k < NBINS; k += 32)
+    if (basis[static_cast<long long>(m) * NBINS + k] != 0.f) { lo = min(lo, k); hi = max(hi, k); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { band[2 * m] = hi >= 0 ? lo : 0; band[2 * m + 1] = hi >= 0 ? hi + 1 : 0; }
+}
+
+__global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__ y, int N, int F,
+                                                       const float* __restrict__ basis, const int32_t* __restrict__ band,
+                                                       int n_mels, float* __restrict__ mel, float* __restrict__ energy) {
+  extern __shared__ __align__(16) uint8_t stft_smem[];
+  float2 (*buf)[2][HALF] = reinterpret_cast<float2 (*)[2][HALF]>(stft_smem);             // [4][2][512]
+  float2* tw = reinterpret_cast<float2*>(stft_smem + sizeof(float2) * 4 * 2 * HALF);      // W_1024^k, k < 512
+  float (*mag)[NBINS + 3] = reinterpret_cast<float (*)[NBINS + 3]>(tw + HALF);            // [FPB][516]
+  float* samp = reinterpret_cast<float*>(mag + FPB);                                      // [NSAMP]
+  const int b = blockIdx.y, f0 = blockIdx.x * FPB;
+  const float* yb = y + static_cast<long long>(b) * N;
+  for (int i = threadIdx.x; i < NSAMP; i += 256) {
+    int src = f0 * HOP + i - NFFT / 2;         // reflect padding (F.pad mode='reflect', stft.py:58-62)
+    if (src < 0) src = -src;
+    if (src >= N) src = 2 * (N - 1) - src;
+    samp[i] = (src >= 0 && src < N) ? yb[src] : 0.f;
+  }
+  for (int k = threadIdx.x; k < HALF; k += 256) {
+    float s, c;
+    sincospif(-static_cast<float>(k) / 512.0f, &s, &c);
+    tw[k] = make_float2(c, s);
+  }
+  __syncthreads();
+
+  const int grp = threadIdx.x >> 6, lt = threadIdx.x & 63;   // 4 frames in flight, 64 threads each
+  for (int round = 0; round < FPB / 4; ++round) {
+    const int fl = round * 4 + grp;                          // local frame index
+    float2* d0 = buf[grp][0];
+    float2* d1 = buf[grp][1];
+    // window + pack real pairs into complex: z[n] = x[2n] + i x[2n+1]
+    for (int n = lt; n < HALF; n += 64) {
+      const int i0 = 2 * n, i1 = 2 * n + 1;
+      const float c0 = i0 < HALF ? tw[i0].x : -tw[i0 - HALF].x;   // cos(2*pi*i/1024)
+      const float c1 = i1 < HALF ? tw[i1].x : -tw[i1 - HALF].x;
+      const float w0 = 0.5f - 0.5f * c0, w1 = 0.5f - 0.5f * c1;
+      d0[n] = make_float2(samp[fl * HOP + i0] * w0, samp[fl * HOP + i1] * w1);
+    }
+    __syncthreads();
+    // 512-point Stockham radix-2: 9 passes, 256 butterflies each
+#pragma unroll 1
+    for (int s = 0; s < 9; ++s) {
+      const int Ns = 1 << s;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int jdx = lt + q * 64;
+        const int k = jdx & (Ns - 1);
+        const float2 w = tw[k * (HALF / Ns)];
+        const float2 a = d0[jdx], bb = d0[jdx + 256];
+        const float2 bw = make_float2(bb.x * w.x - bb.y * w.y, bb.x * w.y + bb.y * w.x);
+        const int dst = ((jdx - k) << 1) + k;
+        d1[dst] = make_float2(a.x + bw.x, a.y + bw.y);
+        d1[dst + Ns] = make_float2(a.x - bw.x, a.y - bw.y);
+      }
+      __syncthreads();
+      float2* tmp = d0; d0 = d1; d1 = tmp;
+    }
+    // split post-pass: X[k] = E + W^k * O, k = 0..512
+    for (int k = lt; k <= HALF; k += 64) {
+      const float2 zk = d0[k & (HALF - 1)];
+      const float2 zr = d0[(HALF - k) & (HALF - 1)];
+      const float2 zc = make_float2(zr.x, -zr.y);
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+      const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
+      const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);       // -i/2 * d
+      const float2 w = k < HALF ? tw[k] : make_float2(-1.f, 0.f);
+      const float xr = e.x + (o.x * w.x - o.y * w.y);
+      const float xi = e.y + (o.x * w.y + o.y * w.x);
+      mag[fl][k] = sqrtf(xr * xr + xi * xi);
+    }
+    __syncthreads();
+  }
+
+  // energy: L2 norm over the 513 bins (stft.py:158); warp per frame
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < FPB && f0 + warp < F) {
+    float s = 0.f;
+    for (int k = lane; k < NBINS; k += 32) s += mag[warp][k] * mag[warp][k];
+    s = warp_sum(s);
+    if (lane == 0) energy[static_cast<long long>(b) * F + f0 + warp] = sqrtf(s);
+  }
+  // mel projection + log compression (stft.py:156-157)
+  for (int i = threadIdx.x; i < n_mels * FPB; i += 256) {
+    const int m = i / FPB, fl = i % FPB;
+    if (f0 + fl >= F) continue;
+    const int lo = band[2 * m], hi = band[2 * m + 1];
+    const float* br = basis + static_cast<long long>(m) * NBINS;
+    float acc = 0.f;
+    for (int k = lo; k < hi; ++k) acc = fmaf(br[k], mag[fl][k], acc);
+    mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = logf(fmaxf(acc, 1e-5f));
+  }
+}
+
+}  // namespace
+}  // namespace sb
+
+extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
+                                   int32_t* band_ws, float* mel, float* energy, void* stream) {
+  using namespace sb;
+  SB_REQUIRE(y && mel_basis && band_ws && mel && energy, "stft_mel: null pointer");
+  SB_REQUIRE(B > 0 && N > NFFT / 2 && n_mels > 0 && n_mels <= 256, "stft_mel: bad shape (B=%d N=%d n_mels=%d)", B, N, n_mels);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int F = 1 + N / HOP;
+  mel_band_kernel<<<ceil_div(n_mels, 8), 256, 0, s>>>(mel_basis, n_mels, band_ws);
+  SB_LAUNCH_OK();
+  dim3 grid(ceil_div(F, FPB), B);
+  constexpr size_t smem = sizeof(float2) * 4 * 2 * HALF + sizeof(float2) * HALF + sizeof(float) * FPB * (NBINS + 3) +
+                          sizeof(float) * NSAMP;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA_OK(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  stft_mel_kernel<<<grid, 256, smem, s>>>(y, N, F, mel_basis, band_ws, n_mels, mel, energy);
+  SB_LAUNCH_OK();
+  return 0;
+}

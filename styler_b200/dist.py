@@ -1,0 +1,54 @@
+"""Data-parallel plumbing: one process per GPU (torchrun), utterances sharded across ranks with no data-path
+collective; the only exchange is the final gather of the mel tensors (and lengths) to rank 0 over NCCL/NVLink,
+replacing nn.DataParallel's gather (train.py:33, synthesize.py:62 of the reference).  Every utterance is independent
+in eval mode; to stay bitwise identical to a single-GPU run all ranks must pad to the same
+max_src_len / max_mel_len, which the caller passes explicitly (both are forward() arguments)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of n_items utterances for `rank` (remainder spread over the first ranks)."""
+    q, r = divmod(n_items, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def shard_batch(batch, rank, world):
+    """Slice every per-utterance tensor of a forward() kwargs/args dict along dim 0."""
+    n = batch["src_seq"].shape[0]
+    lo, hi = shard_range(n, rank, world)
+    return {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == n else v) for k, v in batch.items()}
+
+
+def gather_to_rank0(tensors, dst=0):
+    """Gather same-shaped per-rank tensors to `dst` (concatenated along dim 0 there, None elsewhere).
+    All ranks must hold equal shapes (equal shard sizes and the global padded T)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(tensors)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    outs = []
+    for t in tensors:
+        t = t.contiguous()
+        bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, bufs, dst=dst)
+        outs.append(torch.cat(bufs, dim=0) if rank == dst else None)
+    return outs

@@ -1,0 +1,334 @@
+"""Host-side orchestration of the STYLER forward over the C-ABI kernels (no torch compute on the hot path).
+
+`Engine` packs a reference-format state_dict once into kernel layouts (conv weights as [taps][N][Cin], fused QKV with
+1/temperature folded into W_q, BatchNorm folded into the PostNet convs, one-hot conv tables, stacked LSTM weights) and
+then runs the eval-mode forward of styler.py:39-58 / modules.py:311-387 as a sequence of kernel launches on the current
+CUDA stream.  Precision modes:
+  "bf16": bf16 activations/weights, tcgen05 kind::f16, fp32 accumulate / LayerNorm / softmax / LSTM state (throughput mode)
+  "tf32": fp32 activations/weights, tcgen05 kind::tf32 (fp32-parity mode on tensor cores)
+  "fp32": fp32 activations/weights, CUDA-core fp32 kernels only (exact-fp32 parity mode, slow)
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import ACT_RELU, ACT_TANH, IMPL_AUTO, IMPL_SIMT, IMPL_TC
+
+MAX_SEQ_LEN = 1000  # hparams.max_seq_len (Models.py:69,120)
+
+
+def sinusoid_table(n_position, d_hid=256):
+    """transformer/Models.py:11-30 (float64 table cast to float32), vectorised."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)
+    angle = pos / np.power(10000.0, 2.0 * (j // 2) / d_hid)[None, :]
+    tab = angle.copy()
+    tab[:, 0::2] = np.sin(angle[:, 0::2])
+    tab[:, 1::2] = np.cos(angle[:, 1::2])
+    return torch.from_numpy(tab).float()
+
+
+class _NS(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class Engine:
+    def __init__(self, state_dict, device, precision="bf16"):
+        if precision not in ("bf16", "tf32", "fp32"):
+            raise ValueError("precision must be bf16 | tf32 | fp32")
+        self.precision = precision
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("styler_b200.Engine needs a CUDA device: the product path has no CPU implementation")
+        self.dt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.impl = IMPL_SIMT if precision == "fp32" else IMPL_AUTO
+        self.attn_impl = IMPL_SIMT if precision == "fp32" else IMPL_TC
+        self._pos_cache = {}
+        self.inter = {}
+        self.prof = None   # bench.py: list collecting (start_event, end_event, B, T) around the dominant kernel (FFN conv k9)
+        self._pack({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _f32(self, t):
+        return t.detach().to(self.device, torch.float32).contiguous()
+
+    def _w(self, t):
+        """Conv1d weight [N,Cin,KS] (or Linear [N,Cin]) -> [KS,N,Cin] in the activation dtype."""
+        t = t.detach().to(self.device, torch.float32)
+        if t.dim() == 2:
+            t = t.unsqueeze(-1)
+        return t.permute(2, 0, 1).contiguous().to(self.dt)
+
+    def _pack_fft(self, sd, p):
+        W = _NS()
+        a = p + "slf_attn."
+        inv_temp = 1.0 / math.sqrt(64.0)   # temperature sqrt(d_k) (SubLayers.py:24); power of two -> exact fold
+        wq = sd[a + "w_qs.weight"].to(self.device, torch.float32) * inv_temp
+        bq = sd[a + "w_qs.bias"].to(self.device, torch.float32) * inv_temp
+        W.wqkv = self._w(torch.cat([wq, sd[a + "w_ks.weight"].to(self.device), sd[a + "w_vs.weight"].to(self.device)], 0))
+        W.bqkv = self._f32(torch.cat([bq, sd[a + "w_ks.bias"].to(self.device), sd[a + "w_vs.bias"].to(self.device)], 0))
+        W.wfc, W.bfc = self._w(sd[a + "fc.weight"]), self._f32(sd[a + "fc.bias"])
+        W.ln1 = (self._f32(sd[a + "layer_norm.weight"]), self._f32(sd[a + "layer_norm.bias"]))
+        f = p + "pos_ffn."
+        W.w1, W.b1 = self._w(sd[f + "w_1.weight"]), self._f32(sd[f + "w_1.bias"])
+        W.w2, W.b2 = self._w(sd[f + "w_2.weight"]), self._f32(sd[f + "w_2.bias"])
+        W.pad1 = (sd[f + "w_1.weight"].shape[2] - 1) // 2
+        W.ln2 = (self._f32(sd[f + "layer_norm.weight"]), self._f32(sd[f + "layer_norm.bias"]))
+        return W
+
+    def _pack_predictor(self, sd, p):
+        W = _NS()
+        q = p + "conv_layer."
+        W.c1, W.b1 = self._w(sd[q + "conv1d_1.conv.weight"]), self._f32(sd[q + "conv1d_1.conv.bias"])
+        W.c2, W.b2 = self._w(sd[q + "conv1d_2.conv.weight"]), self._f32(sd[q + "conv1d_2.conv.bias"])
+        W.ln1 = (self._f32(sd[q + "layer_norm_1.weight"]), self._f32(sd[q + "layer_norm_1.bias"]))
+        W.ln2 = (self._f32(sd[q + "layer_norm_2.weight"]), self._f32(sd[q + "layer_norm_2.bias"]))
+        W.lw = self._f32(sd[p + "linear_layer.weight"].reshape(-1))
+        W.lb = float(sd[p + "linear_layer.bias"].reshape(-1)[0].item())
+        return W
+
+    def _pack(self, sd):
+        P, SE = "style_modeling.", "style_modeling.style_encoder."
+        w = _NS()
+        te = SE + "text_encoder."
+        w.emb = self._f32(sd[te + "src_word_emb.weight"])
+        w.enc_pos = self._f32(sd[te + "position_enc"][0])
+        w.dec_pos = self._f32(sd["decoder.position_enc"][0])
+        w.enc_layers = [self._pack_fft(sd, "%slayer_stack.%d." % (te, i)) for i in range(2)]
+        w.dec_layers = [self._pack_fft(sd, "decoder.layer_stack.%d." % i) for i in range(4)]
+        ae = SE + "audio_encoder."
+        w.branches = []
+        for n in (1, 2, 3, 4):
+            br = _NS(convs=[], onehot=n in (2, 3))
+            for j in range(3):
+                q = "%sconvolutions_%d.%d." % (ae, n, j)
+                cw = sd[q + "0.conv.weight"]
+                if j == 0 and br.onehot:   # [C,257,5] -> gather table [5,257,C] fp32
+                    cwp = self._f32(cw.permute(2, 1, 0))
+                else:
+                    cwp = self._w(cw)
+                br.convs.append((cwp, self._f32(sd[q + "0.conv.bias"]), self._f32(sd[q + "1.weight"]),
+                                 self._f32(sd[q + "1.bias"])))
+            L = "%slstm_%d." % (ae, n)
+            br.lstm = []
+            for layer in range(2):
+                k, kr = "l%d" % layer, "l%d_reverse" % layer
+                wih = torch.cat([sd[L + "weight_ih_" + k], sd[L + "weight_ih_" + kr]], 0)
+                bias = torch.cat([sd[L + "bias_ih_" + k] + sd[L + "bias_hh_" + k],
+                                  sd[L + "bias_ih_" + kr] + sd[L + "bias_hh_" + kr]], 0)
+                whh = torch.stack([sd[L + "weight_hh_" + k], sd[L + "weight_hh_" + kr]], 0)
+                br.lstm.append((self._w(wih), self._f32(bias), self._f32(whh)))
+            w.branches.append(br)
+        w.tld = (self._w(sd[SE + "text_linear_down.0.weight"]), self._f32(sd[SE + "text_linear_down.0.bias"]))
+        w.slp = (self._w(sd[SE + "speaker_linear_p.0.weight"]), self._f32(sd[SE + "speaker_linear_p.0.bias"]))
+        w.sl = (self._w(sd[SE + "speaker_linear.0.weight"]), self._f32(sd[SE + "speaker_linear.0.bias"]))
+        w.cls = {}
+        for n in ("d", "p", "e"):
+            q = "%saugmentation_classifier_%s.classifier." % (P, n)
+            w.cls[n] = (self._w(sd[q + "d_fc1.weight"]), self._f32(sd[q + "d_fc1.bias"]),
+                        (self._f32(sd[q + "d_bn1.weight"]), self._f32(sd[q + "d_bn1.bias"])),
+                        self._f32(sd[q + "d_fc2.weight"]), self._f32(sd[q + "d_fc2.bias"]))
+        w.mlp = {}
+        for n in ("duration", "pitch", "energy", "residual"):
+            q = "%s%s_linear." % (P, n)
+            w.mlp[n] = (self._w(sd[q + "0.weight"]), self._f32(sd[q + "0.bias"]), self._w(sd[q + "2.weight"]),
+                        self._f32(sd[q + "2.bias"]))
+        w.tlu = (self._w(sd[P + "text_linear_up.0.weight"]), self._f32(sd[P + "text_linear_up.0.bias"]))
+        w.pred = {n: self._pack_predictor(sd, "%s%s_predictor." % (P, n)) for n in ("duration", "pitch", "energy")}
+        w.pitch_bins, w.energy_bins = self._f32(sd[P + "pitch_bins"]), self._f32(sd[P + "energy_bins"])
+        w.pitch_emb, w.energy_emb = self._f32(sd[P + "pitch_embedding.weight"]), self._f32(sd[P + "energy_embedding.weight"])
+        w.mel = (self._w(sd["mel_linear.weight"]), self._f32(sd["mel_linear.bias"]))
+        w.postnet = []
+        for j in range(5):   # fold eval-mode BatchNorm1d into the conv (Layers.py:91-119,121-130)
+            q = "postnet.convolutions.%d." % j
+            cw, cb = sd[q + "0.conv.weight"].to(self.device, torch.float32), sd[q + "0.conv.bias"].to(self.device, torch.float32)
+            g, be = sd[q + "1.weight"].to(self.device, torch.float32), sd[q + "1.bias"].to(self.device, torch.float32)
+            rm, rv = sd[q + "1.running_mean"].to(self.device, torch.float32), sd[q + "1.running_var"].to(self.device, torch.float32)
+            scale = g / torch.sqrt(rv + 1e-5)
+            w.postnet.append((self._w(cw * scale[:, None, None]), self._f32((cb - rm) * scale + be)))
+        self.w = w
+
+    # ------------------------------------------------------------------------------------------ building blocks
+    def _pos(self, which, n):
+        """Position rows [n,256] fp32: stored table up to max_seq_len, rebuilt (and cached) beyond (Models.py:69-74)."""
+        base = self.w.enc_pos if which == "enc" else self.w.dec_pos
+        if n <= MAX_SEQ_LEN:
+            return base[:n]
+        if n not in self._pos_cache:
+            self._pos_cache[n] = sinusoid_table(n).to(self.device)
+        return self._pos_cache[n]
+
+    def fft_block(self, x, lens, W, out=None):
+        """transformer/Layers.py:26-34: MHA -> zero padded rows -> Conv1d FFN -> zero padded rows."""
+        B, T, _ = x.shape
+        Tp = (T + 7) // 8 * 8
+        qk = torch.empty(B, T, 512, device=x.device, dtype=self.dt)
+        vt = torch.empty(B, 256, Tp, device=x.device, dtype=self.dt)
+        ops.conv1d(x, W.wqkv, W.bqkv, out=qk, vt=vt, vt_col0=512, impl=self.impl)
+        ctx = ops.attention(qk, vt, lens, 4, impl=self.attn_impl)
+        y1 = ops.conv1d(ctx, W.wfc, W.bfc, residual=x, ln=W.ln1, lens=lens, impl=self.impl)
+        if self.prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        h = ops.conv1d(y1, W.w1, W.b1, pad=W.pad1, act=ACT_RELU, impl=self.impl)
+        if self.prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.prof.append((e0, e1, B, T))
+        return ops.conv1d(h, W.w2, W.b2, residual=y1, ln=W.ln2, lens=lens, out=out, impl=self.impl)
+
+    def text_encoder(self, src_seq, src_len, out=None):
+        """transformer/Models.py:60-84."""
+        L = src_seq.shape[1]
+        x = ops.embed_pos(src_seq, self.w.emb, self._pos("enc", L), self.dt)
+        x = self.fft_block(x, src_len, self.w.enc_layers[0])
+        return self.fft_block(x, src_len, self.w.enc_layers[1], out=out)
+
+    def predictor(self, x, lens, W):
+        """modules.py:457-465: Conv k3 + ReLU + LN, Conv k3 + ReLU + LN, Linear(256->1), masked_fill."""
+        h = ops.conv1d(x, W.c1, W.b1, pad=1, act=ACT_RELU, ln=W.ln1, impl=self.impl)
+        _, d = ops.conv1d(h, W.c2, W.b2, pad=1, act=ACT_RELU, ln=W.ln2, lens=lens, dot=(W.lw, W.lb),
+                          want_out=self.precision == "fp32", impl=self.impl)
+        return d
+
+    def audio_encoder(self, mel_target, p_idx, e_idx, mel_aug, mel_len, src_len, L):
+        """modules.py:164-201 on the padded grid: conv stacks + GroupNorm + ReLU @Tr, Mel Calibrator, 2-layer BiLSTMs @L."""
+        outs = []
+        ins = (mel_target, p_idx, e_idx, mel_aug)
+        for br, xin in zip(self.w.branches, ins):
+            x = None
+            for j, (cw, cb, g, be) in enumerate(br.convs):
+                if j == 0 and br.onehot:
+                    x = ops.onehot_conv(xin, cw, cb, self.dt)
+                else:
+                    x = ops.conv1d(xin if j == 0 else x, cw, cb, pad=2, impl=self.impl)
+                ops.groupnorm_relu_(x, g, be, 16, 1e-5)
+            c = ops.mel_calibrator(x, mel_len, src_len, L)
+            for (wih, bias, whh) in br.lstm:
+                B = c.shape[0]
+                gx = torch.empty(B, L, wih.shape[1], device=c.device, dtype=torch.float32)
+                ops.conv1d(c, wih, bias, out_f32=gx, want_out=False, impl=self.impl)
+                c = ops.bilstm_layer(gx, whh, self.dt)
+            outs.append(c)
+        return outs
+
+    def _mlp2(self, x, W, out=None):
+        h = ops.conv1d(x, W[0], W[1], act=ACT_RELU, impl=self.impl)
+        return ops.conv1d(h, W[2], W[3], act=ACT_RELU, out=out, impl=self.impl)
+
+    def _classifier(self, x, W):
+        h = ops.conv1d(x, W[0], W[1], ln=W[2], act2=ACT_RELU, impl=self.impl)
+        return ops.classifier_tail(h, W[3], W[4])
+
+    def _act(self, t):
+        """fp32 user tensor -> activation dtype (no-op view in the fp32 modes)."""
+        t = t.to(self.device, torch.float32).contiguous()
+        return t if self.dt == torch.float32 else ops.cast(t, self.dt)
+
+    # ------------------------------------------------------------------------------------------ decode (styler.py:29-37)
+    def decode(self, x, mel_lens):
+        """x [B,T,256] (activation dtype) -> (mel fp32 [B,T,80], mel_postnet fp32 [B,T,80])."""
+        B, T, _ = x.shape
+        h = ops.add(x, pos=self._pos("dec", T))
+        for W in self.w.dec_layers:
+            h = self.fft_block(h, mel_lens, W)
+        mel = torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
+        if self.dt == torch.float32:
+            ops.conv1d(h, self.w.mel[0], self.w.mel[1], out=mel, impl=self.impl)
+            mel_t = mel
+        else:
+            mel_t = ops.conv1d(h, self.w.mel[0], self.w.mel[1], out_f32=mel, impl=self.impl)
+        p = mel_t
+        for j in range(4):
+            p = ops.conv1d(p, self.w.postnet[j][0], self.w.postnet[j][1], pad=2, act=ACT_TANH, impl=self.impl)
+        post = torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
+        ops.conv1d(p, self.w.postnet[4][0], self.w.postnet[4][1], pad=2, residual_f32=mel, out_f32=post, want_out=False,
+                   impl=self.impl)
+        return mel, post
+
+    # ------------------------------------------------------------------------------------------ style modeling
+    def encode(self, src_seq, speaker_embed, mel_target, mel_aug, p_norm, e_input, src_len, mel_len):
+        """StyleEncoder.forward + the L-level part of StyleModeling.forward (modules.py:225-235,311-353).
+        Returns the [B,L,1280] concatenated encodings, log-duration prediction and the DAT posteriors."""
+        w = self.w
+        B, L = src_seq.shape
+        dev = self.device
+        enc = torch.empty(B, L, 1280, device=dev, dtype=self.dt)
+        text = self.text_encoder(src_seq, src_len, out=enc[..., 0:256])
+        neck = ops.conv1d(text, w.tld[0], w.tld[1], act=ACT_RELU, impl=self.impl)                      # [B,L,4]
+        spk_in = self._act(speaker_embed).unsqueeze(0)                                                  # [1,B,512]
+        spk_p = ops.conv1d(spk_in, w.slp[0], w.slp[1], act=ACT_RELU, impl=self.impl)[0]                 # [B,128]
+        spk = ops.conv1d(spk_in, w.sl[0], w.sl[1], act=ACT_RELU, impl=self.impl)[0]                     # [B,256]
+        p_idx, e_idx = ops.quantize_index(p_norm), ops.quantize_index(e_input)                          # utils.py:417-429
+        d_enc, p_enc, e_enc, n_enc = self.audio_encoder(self._act(mel_target), p_idx, e_idx, self._act(mel_aug),
+                                                        mel_len, src_len, L)
+        post = tuple(self._classifier(x, w.cls[n]) for x, n in ((d_enc, "d"), (p_enc, "p"), (e_enc, "e")))
+        p_enc_sp = ops.add(p_enc, rowvec=spk_p)                                                         # modules.py:332
+        d_up = self._mlp2(d_enc, w.mlp["duration"])
+        p_up = self._mlp2(p_enc_sp, w.mlp["pitch"])
+        e_up = self._mlp2(e_enc, w.mlp["energy"])
+        n_up = self._mlp2(n_enc, w.mlp["residual"], out=enc[..., 1024:1280])
+        neck_up = ops.conv1d(neck, w.tlu[0], w.tlu[1], act=ACT_RELU, impl=self.impl)                    # [B,L,256]
+        ops.add(neck_up, p_up, out=enc[..., 256:512])                                                   # modules.py:350
+        ops.add(None, rowvec=spk, out=enc[..., 512:768])
+        ops.add(neck_up, e_up, out=enc[..., 768:1024])
+        dur_in = ops.add(neck_up, d_up)
+        log_d = self.predictor(dur_in, src_len, w.pred["duration"])                                     # modules.py:353
+        self.inter = dict(text_encoding=text, text_encoding_neck=neck_up, pitch_encoding=p_enc, speaker_encoding=spk,
+                          speaker_encoding_p=spk_p, duration_encoding=d_up, energy_encoding=e_up, noise_encoding=n_up,
+                          pitch_up=p_up, max_seq_len=L)
+        return enc, log_d, post
+
+    def variance_adapt(self, enc, log_d, T, mel_lens_for_mask, d_target=None, p_target=None, e_target=None,
+                       d_control=1.0, p_control=1.0, e_control=1.0, duration=None):
+        """LengthRegulator + pitch/energy predictors + bucketize/embedding sum (modules.py:355-385).
+        `duration` (already rounded, fp32) or d_target (int64) drives the expand to T frames."""
+        w = self.w
+        dur = d_target if d_target is not None else duration
+        encT, mel_len, cum = ops.length_regulator(enc, dur, T)
+        lens = mel_lens_for_mask if mel_lens_for_mask is not None else mel_len
+        e_pred = self.predictor(encT[..., 768:1024], lens, w.pred["energy"])
+        p_in = ops.add(encT[..., 256:512], encT[..., 512:768])
+        p_pred = self.predictor(p_in, lens, w.pred["pitch"])
+        p_val, p_scale = (p_target.to(self.device, torch.float32).contiguous(), 1.0) if p_target is not None else (p_pred, float(p_control))
+        e_val, e_scale = (e_target.to(self.device, torch.float32).contiguous(), 1.0) if e_target is not None else (e_pred, float(e_control))
+        x, x_noisy, _, _ = ops.bucket_embed_sum(encT[..., 0:256], encT[..., 512:768], encT[..., 1024:1280], p_val, e_val,
+                                                p_scale, e_scale, w.pitch_bins, w.energy_bins, w.pitch_emb, w.energy_emb,
+                                                want_noisy=True)
+        return x, x_noisy, encT, p_pred, e_pred, mel_len
+
+    def forward(self, src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target=None, p_target=None,
+                e_target=None, max_src_len=None, max_mel_len=None, speaker_embed=None, d_control=1.0, p_control=1.0,
+                e_control=1.0):
+        """styler.py:39-58.  Returns the reference's 9-tuple (mels/predictions fp32, masks bool, lengths int64)."""
+        dev = self.device
+        src_seq = src_seq.to(dev).contiguous()
+        src_len = src_len.to(dev, torch.int64).contiguous()
+        mel_len = mel_len.to(dev, torch.int64).contiguous()
+        p_norm = p_norm.to(dev, torch.float32).contiguous()
+        e_input = e_input.to(dev, torch.float32).contiguous()
+        B, L = src_seq.shape
+        if max_src_len is not None and max_src_len != L:
+            raise ValueError("max_src_len (%d) must equal the padded text length (%d)" % (max_src_len, L))
+        enc, log_d, post = self.encode(src_seq, speaker_embed, mel_target, mel_aug, p_norm, e_input, src_len, mel_len)
+        if d_target is not None:                                   # teacher forcing (styler.py:44-46)
+            d_target = d_target.to(dev, torch.int64).contiguous()
+            T = int(max_mel_len) if max_mel_len else int(mel_len.max().item())
+            x, x_noisy, _, p_pred, e_pred, _ = self.variance_adapt(enc, log_d, T, mel_len, d_target, p_target, e_target,
+                                                                   d_control, p_control, e_control)
+            out_len = mel_len
+        else:                                                      # free running (styler.py:47-49, modules.py:357-360)
+            duration = ops.duration_round(log_d, 1.0, float(d_control))
+            tot, _ = ops.length_regulator_scan(duration)
+            T = int(max_mel_len) if max_mel_len else int(tot.max().item())     # the one host sync of the path
+            x, x_noisy, _, p_pred, e_pred, out_len = self.variance_adapt(enc, log_d, T, None, None, p_target, e_target,
+                                                                         d_control, p_control, e_control, duration=duration)
+        mel, post_mel = self.decode(x, out_len)
+        mel_n, post_mel_n = self.decode(x_noisy, out_len)
+        ar = torch.arange(L, device=dev)
+        src_mask = ar.unsqueeze(0) >= src_len.unsqueeze(1)
+        mel_mask = torch.arange(T, device=dev).unsqueeze(0) >= out_len.unsqueeze(1)
+        return (mel, mel_n), (post_mel, post_mel_n), log_d, p_pred, e_pred, src_mask, mel_mask, out_len, post

@@ -1,0 +1,299 @@
+"""Drop-in `STYLER` nn.Module: the reference's constructor, forward()/decode() signatures, submodule tree and
+328-key state_dict (styler.py:13-58, modules.py, transformer/*.py), with the eval-mode forward executed by
+hand-written sm_100a kernels through the C ABI (styler_b200.engine.Engine).
+
+The torch.nn modules below are PARAMETER CONTAINERS only (they give `load_state_dict` / `state_dict` / `.to()` the
+reference's exact key surface, Appendix D of SURVEY.md); none of their torch forward code runs on the product path.
+Training (backward, dropout, batch-stat BatchNorm) is out of scope: calling forward in training mode raises.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import hparams as hp
+from .engine import Engine, sinusoid_table
+
+N_SRC_VOCAB = 152  # len(text.symbols) + 1 (transformer/Models.py:37)
+
+
+# --------------------------------------------------------------------------------------------- containers
+class _Container(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("%s is a parameter container; the computation runs in styler_b200.engine" % type(self).__name__)
+
+
+class MultiHeadAttention(_Container):      # transformer/SubLayers.py:9-29
+    def __init__(self, n_head, d_model, d_k, d_v):
+        super().__init__()
+        self.w_qs, self.w_ks, self.w_vs = nn.Linear(d_model, n_head * d_k), nn.Linear(d_model, n_head * d_k), nn.Linear(d_model, n_head * d_v)
+        self.layer_norm = nn.LayerNorm(d_model)
+        self.fc = nn.Linear(n_head * d_v, d_model)
+
+
+class PositionwiseFeedForward(_Container):  # transformer/SubLayers.py:64-79
+    def __init__(self, d_in, d_hid):
+        super().__init__()
+        k = hp.fft_conv1d_kernel_size
+        self.w_1 = nn.Conv1d(d_in, d_hid, kernel_size=k[0], padding=(k[0] - 1) // 2)
+        self.w_2 = nn.Conv1d(d_hid, d_in, kernel_size=k[1], padding=(k[1] - 1) // 2)
+        self.layer_norm = nn.LayerNorm(d_in)
+
+
+class FFTBlock(_Container):                 # transformer/Layers.py:10-24
+    def __init__(self, d_model, d_inner, n_head, d_k, d_v):
+        super().__init__()
+        self.slf_attn = MultiHeadAttention(n_head, d_model, d_k, d_v)
+        self.pos_ffn = PositionwiseFeedForward(d_model, d_inner)
+
+
+def _fft_stack(n_layers, d_model, n_head):
+    return nn.ModuleList([FFTBlock(d_model, hp.fft_conv1d_filter_size, n_head, d_model // n_head, d_model // n_head)
+                          for _ in range(n_layers)])
+
+
+class Encoder(_Container):                  # transformer/Models.py:33-58
+    def __init__(self):
+        super().__init__()
+        self.src_word_emb = nn.Embedding(N_SRC_VOCAB, hp.encoder_hidden, padding_idx=0)
+        self.position_enc = nn.Parameter(sinusoid_table(hp.max_seq_len + 1, hp.encoder_hidden).unsqueeze(0), requires_grad=False)
+        self.layer_stack = _fft_stack(hp.encoder_layer, hp.encoder_hidden, hp.encoder_head)
+
+
+class Decoder(_Container):                  # transformer/Models.py:87-109
+    def __init__(self):
+        super().__init__()
+        self.position_enc = nn.Parameter(sinusoid_table(hp.max_seq_len + 1, hp.decoder_hidden).unsqueeze(0), requires_grad=False)
+        self.layer_stack = _fft_stack(hp.decoder_layer, hp.decoder_hidden, hp.decoder_head)
+
+
+class ConvNorm(_Container):                 # transformer/Layers.py:37-64
+    def __init__(self, cin, cout, kernel_size):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, kernel_size=kernel_size, padding=(kernel_size - 1) // 2)
+
+
+class PostNet(_Container):                  # transformer/Layers.py:67-119
+    def __init__(self, n_mel=80, dim=512, ks=5, n=5):
+        super().__init__()
+        chans = [n_mel] + [dim] * (n - 1) + [n_mel]
+        self.convolutions = nn.ModuleList([nn.Sequential(ConvNorm(chans[i], chans[i + 1], ks), nn.BatchNorm1d(chans[i + 1]))
+                                           for i in range(n)])
+
+
+class EncoderInput(tuple):
+    """What `StyleEncoder.encoder_input_cat` returns here: (mel_target, p_index, e_index, mel_aug) instead of the
+    reference's dense [B,674,Tr] one-hot tensor (modules.py:218-223); `AudioEncoder.forward` consumes it."""
+
+
+class AudioEncoder(_Container):             # modules.py:84-162
+    def __init__(self, owner):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)
+        dims = ((hp.n_mel_channels, hp.va_enc_dim_d, hp.va_neck_hidden_d), (hp.va_dim_f0, hp.va_enc_dim_p, hp.va_neck_hidden_p),
+                (hp.va_dim_energy, hp.va_enc_dim_e, hp.va_neck_hidden_e), (hp.n_mel_channels, hp.va_enc_dim_r, hp.va_neck_hidden_r))
+        for n, (cin, c, h) in enumerate(dims, start=1):
+            setattr(self, "convolutions_%d" % n, nn.ModuleList(
+                [nn.Sequential(ConvNorm(cin if j == 0 else c, c, 5), nn.GroupNorm(c // hp.va_chs_grp, c)) for j in range(3)]))
+            setattr(self, "lstm_%d" % n, nn.LSTM(c, h, 2, batch_first=True, bidirectional=True))
+
+    def forward(self, cat, len_org, seq_len, mask=None):
+        """modules.py:164-201; `cat` is the EncoderInput from StyleEncoder.encoder_input_cat."""
+        eng = self._owner._engine_for(cat[0])
+        mel_t, p_idx, e_idx, mel_a = cat
+        L = int(seq_len.max().item())
+        return tuple(eng.audio_encoder(eng._act(mel_t), p_idx, e_idx, eng._act(mel_a), len_org.to(eng.device), seq_len.to(eng.device), L))
+
+
+class StyleEncoder(_Container):             # modules.py:204-216
+    def __init__(self, owner):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)
+        self.text_encoder = Encoder()
+        self.audio_encoder = AudioEncoder(owner)
+        self.text_linear_down = nn.Sequential(nn.Linear(hp.encoder_hidden, hp.va_neck_hidden_t), nn.ReLU())
+        self.speaker_linear_p = nn.Sequential(nn.Linear(hp.speaker_embed_dim, hp.va_neck_hidden_p * 2), nn.ReLU())
+        self.speaker_linear = nn.Sequential(nn.Linear(hp.speaker_embed_dim, hp.encoder_hidden), nn.ReLU())
+
+    def encoder_input_cat(self, mel_target, p_norm, e_input, mel_aug):
+        from . import ops
+        eng = self._owner._engine_for(mel_target)
+        return EncoderInput((mel_target, ops.quantize_index(p_norm.to(eng.device, torch.float32)),
+                             ops.quantize_index(e_input.to(eng.device, torch.float32)), mel_aug))
+
+
+class AugmentationClassifier(_Container):   # modules.py:23-36
+    def __init__(self, input_dim):
+        super().__init__()
+        self.classifier = nn.Sequential(OrderedDict([
+            ("d_fc1", nn.Linear(input_dim, hp.encoder_hidden)), ("d_bn1", nn.LayerNorm(hp.encoder_hidden)),
+            ("d_relu1", nn.ReLU()), ("d_fc2", nn.Linear(hp.encoder_hidden, 2)), ("d_softmax", nn.LogSoftmax(dim=-1))]))
+
+
+class Conv(_Container):                     # modules.py:468-500
+    def __init__(self, cin, cout, kernel_size, padding):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, kernel_size=kernel_size, padding=padding)
+
+
+class StylePredictor(_Container):           # modules.py:426-455
+    def __init__(self):
+        super().__init__()
+        f, k = hp.style_predictor_filter_size, hp.style_predictor_kernel_size
+        self.conv_layer = nn.Sequential(OrderedDict([
+            ("conv1d_1", Conv(hp.encoder_hidden, f, k, (k - 1) // 2)), ("relu_1", nn.ReLU()), ("layer_norm_1", nn.LayerNorm(f)),
+            ("dropout_1", nn.Dropout(hp.style_predictor_dropout)),
+            ("conv1d_2", Conv(f, f, k, 1)), ("relu_2", nn.ReLU()), ("layer_norm_2", nn.LayerNorm(f)),
+            ("dropout_2", nn.Dropout(hp.style_predictor_dropout))]))
+        self.linear_layer = nn.Linear(f, 1)
+
+
+class LengthRegulator(_Container):          # modules.py:390-423
+    def forward(self, x, duration, max_len):
+        from . import ops
+        T = int(max_len) if max_len else int(ops.length_regulator_scan(duration.contiguous())[0].max().item())
+        out, mel_len, _ = ops.length_regulator(x, duration, T)
+        return out, mel_len
+
+
+def _mlp(i, h):
+    return nn.Sequential(nn.Linear(i, h), nn.ReLU(), nn.Linear(h, h), nn.ReLU())
+
+
+class StyleModeling(_Container):            # modules.py:238-283
+    def __init__(self, owner):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)
+        H = hp.encoder_hidden
+        self.style_encoder = StyleEncoder(owner)
+        self.augmentation_classifier_d = AugmentationClassifier(hp.va_neck_hidden_d * 2)
+        self.augmentation_classifier_p = AugmentationClassifier(hp.va_neck_hidden_p * 2)
+        self.augmentation_classifier_e = AugmentationClassifier(hp.va_neck_hidden_e * 2)
+        self.duration_linear = _mlp(hp.va_neck_hidden_d * 2, H)
+        self.pitch_norm_linear = _mlp(hp.va_neck_hidden_p * 2, H)   # allocated, saved, never used (modules.py:254-257)
+        self.pitch_linear = _mlp(hp.va_neck_hidden_p * 2, H)
+        self.energy_linear = _mlp(hp.va_neck_hidden_e * 2, H)
+        self.residual_linear = _mlp(hp.va_neck_hidden_r * 2, H)
+        self.text_linear_up = nn.Sequential(nn.Linear(hp.va_neck_hidden_t, H), nn.ReLU())
+        self.duration_predictor = StylePredictor()
+        self.length_regulator = LengthRegulator()
+        self.pitch_predictor = StylePredictor()
+        self.energy_predictor = StylePredictor()
+        self.pitch_bins = nn.Parameter(torch.exp(torch.linspace(np.log(hp.f0_min), np.log(hp.f0_max), hp.n_bins - 1)), requires_grad=False)
+        self.energy_bins = nn.Parameter(torch.linspace(hp.energy_min, hp.energy_max, hp.n_bins - 1), requires_grad=False)
+        self.pitch_embedding = nn.Embedding(hp.n_bins, H)
+        self.energy_embedding = nn.Embedding(hp.n_bins, H)
+
+    def _store_inspection(self, eng, src_mask, max_len):
+        """modules.py:328-331,342-348: tensors the reference leaves on `self` for synthesize.py's inspection mode."""
+        it = eng.inter
+        L = it["max_seq_len"]
+        self.max_seq_len = L
+        self.pitch_encoding = it["pitch_encoding"]
+        self.speaker_encoding = it["speaker_encoding"].unsqueeze(1).expand(-1, L, -1)
+        self.speaker_encoding_p = it["speaker_encoding_p"].unsqueeze(1).expand(-1, L, -1)
+        self.text_encoding_neck = it["text_encoding_neck"]
+        self.duration_encoding = it["duration_encoding"]
+        self.energy_encoding = it["energy_encoding"]
+        self.noise_encoding = it["noise_encoding"]
+        self.text_encoding = it["text_encoding"]
+        self.src_mask = src_mask
+        self.max_len = max_len
+
+    def predict_inference(self, text_encoding, pitch_encoding, energy_encoding, duration_encoding, speaker_encoding,
+                          noise_encoding, src_mask, max_len, speaker_normalized=True, d_control=1.0, p_control=1.0,
+                          e_control=1.0):
+        """modules.py:285-309 (used by synthesize.py:171): recombine stored encodings, predict, expand, embed."""
+        from . import ops
+        eng = self._owner._engine_for(text_encoding)
+        dt = eng.dt
+        parts = [t.to(eng.device, dt) for t in (text_encoding, pitch_encoding, speaker_encoding, energy_encoding, noise_encoding)]
+        enc = torch.cat([p.expand(parts[0].shape[0], parts[0].shape[1], -1) for p in parts], dim=-1).contiguous()
+        src_len = (~src_mask).sum(1).to(eng.device, torch.int64)
+        log_d = eng.predictor(duration_encoding.to(eng.device, dt).contiguous(), src_len, eng.w.pred["duration"])
+        duration = ops.duration_round(log_d, hp.log_offset, float(d_control))
+        tot, _ = ops.length_regulator_scan(duration)
+        T = int(max_len) if max_len else int(tot.max().item())
+        encT, mel_len, _ = ops.length_regulator(enc, duration, T)
+        e_pred = eng.predictor(encT[..., 768:1024], mel_len, eng.w.pred["energy"])
+        p_in = encT[..., 256:512] if speaker_normalized else ops.add(encT[..., 256:512], encT[..., 512:768])
+        p_pred = eng.predictor(p_in, mel_len, eng.w.pred["pitch"])
+        # embeddings as separate outputs like the reference: recover them from sums with zero partners
+        zeros = torch.zeros_like(encT[..., 0:256])
+        w = eng.w
+        both, _, _, _ = ops.bucket_embed_sum(zeros, zeros, None, p_pred, e_pred, float(p_control), float(e_control),
+                                             w.pitch_bins, w.energy_bins, w.pitch_emb, w.energy_emb, want_noisy=False)
+        zero_p = torch.full_like(p_pred, -1e30)   # bucket 0 -> subtract its row to isolate the energy embedding
+        e_only, _, _, _ = ops.bucket_embed_sum(zeros, zeros, None, zero_p, e_pred, 1.0, 1.0, w.pitch_bins, w.energy_bins,
+                                               w.pitch_emb, w.energy_emb, want_noisy=False)
+        e_emb = e_only.float() - w.pitch_emb[0]
+        p_emb = both.float() - e_emb
+        mel_mask = torch.arange(T, device=eng.device).unsqueeze(0) >= mel_len.unsqueeze(1)
+        return (encT[..., 0:256], p_emb.to(dt), encT[..., 512:768], e_emb.to(dt), encT[..., 1024:1280], log_d, p_pred, e_pred,
+                mel_mask)
+
+
+# --------------------------------------------------------------------------------------------- the model
+class STYLER(nn.Module):
+    """Drop-in for the reference `styler.STYLER` (styler.py:13-58), eval-mode forward on B200 kernels.
+
+    Extra constructor argument `precision` ("bf16" | "tf32" | "fp32", see engine.py) selects the compute mode; the
+    default follows BASELINE.json's full-forward configuration (bf16).
+    """
+
+    def __init__(self, use_postnet=True, precision="bf16"):
+        super().__init__()
+        if not use_postnet:
+            raise NotImplementedError("use_postnet=False is not built (every reference caller uses the default)")
+        self.precision = precision
+        self.style_modeling = StyleModeling(self)
+        self.decoder = Decoder()
+        self.mel_linear = nn.Linear(hp.decoder_hidden, hp.n_mel_channels)
+        self.use_postnet = use_postnet
+        self.postnet = PostNet()
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    # -- engine lifecycle ------------------------------------------------------------------------------------
+    def _invalidate(self):
+        object.__setattr__(self, "_engine", None)
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def set_precision(self, precision):
+        self.precision = precision
+        self._invalidate()
+        return self
+
+    def _engine_for(self, like=None):
+        dev = self.mel_linear.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("styler_b200.STYLER runs only on a CUDA (sm_100a) device; call .cuda() first -- "
+                               "there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("styler_b200.STYLER implements the eval-mode forward only; call .eval()")
+        if self._engine is None or self._engine.device != dev or self._engine.precision != self.precision:
+            with torch.no_grad():
+                object.__setattr__(self, "_engine", Engine(self.state_dict(), dev, self.precision))
+        return self._engine
+
+    # -- reference API ----------------------------------------------------------------------------------------
+    def decode(self, style_modeling_output, mel_mask):
+        """styler.py:29-37: (mel_output, mel_output_postnet), fp32 [B,T,80]."""
+        eng = self._engine_for()
+        x = style_modeling_output.to(eng.device, eng.dt).contiguous()
+        lens = (~mel_mask.to(eng.device)).sum(1).to(torch.int64)
+        return eng.decode(x, lens)
+
+    @torch.no_grad()
+    def forward(self, src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target=None, p_target=None,
+                e_target=None, max_src_len=None, max_mel_len=None, speaker_embed=None, d_control=1.0, p_control=1.0,
+                e_control=1.0):
+        eng = self._engine_for()
+        out = eng.forward(src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target, p_target, e_target,
+                          max_src_len, max_mel_len, speaker_embed, d_control, p_control, e_control)
+        self.style_modeling._store_inspection(eng, out[5], max_mel_len)
+        return out

@@ -1,0 +1,269 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per entry point of include/styler_b200.h).
+
+Tensors are torch CUDA tensors used purely as device buffers; every function enqueues hand-written CUDA kernels
+on the current stream and returns its output tensor(s).  Activations are [B, T, C] views whose last stride is 1.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, IMPL_AUTO, IMPL_SIMT, IMPL_TC  # noqa: F401
+
+
+def _v3(t, name="tensor"):
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise ValueError("%s must be a [B,T,C] view with unit channel stride, got %s / %s" % (name, tuple(t.shape), t.stride()))
+    return t, int(t.stride(0)), int(t.stride(1))
+
+
+def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=None, residual_f32=None, ln=None, ln_eps=1e-5,
+           act2=ACT_NONE, lens=None, dot=None, out=None, want_out=True, out_f32=None, vt=None, vt_col0=0,
+           impl=IMPL_AUTO):
+    """y = epilogue(conv1d(x, w)) -- see styler_conv1d_fwd.  x [B,T,Cin]; w packed [KS,N,Cin] (same dtype as x).
+
+    residual: [B,T,N] tensor added after `act`; residual_row: [B,N] row broadcast over t instead.
+    ln: (gamma, beta) fp32 -> LayerNorm over N;  dot: (w[N] fp32, bias float) -> also returns the [B,T] fp32 row dot.
+    vt: preallocated [B, N - vt_col0, Tpad] tensor receiving columns >= vt_col0 transposed.
+    Returns out (dtype of x) unless want_out=False; with `dot`, returns (out_or_None, dot_out).
+    """
+    x, x_bs, x_ld = _v3(x, "x")
+    L.require_cuda(x, w)
+    B, T, Cin = x.shape
+    KS, N, Cw = w.shape
+    assert Cw == Cin and w.is_contiguous() and w.dtype == x.dtype, (w.shape, x.shape, w.dtype, x.dtype)
+    a = L.Conv1dArgs()
+    a.x, a.x_bstride, a.x_ld = x.data_ptr(), x_bs, x_ld
+    a.B, a.T, a.Cin = B, T, Cin
+    a.w, a.N, a.KS, a.pad = w.data_ptr(), N, KS, pad
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.act, a.act2 = act, act2
+    keep = [x, w, bias]
+    if residual is not None:
+        r, r_bs, r_ld = _v3(residual, "residual")
+        assert r.dtype == x.dtype and r.shape[0] == B and r.shape[2] >= N
+        a.residual, a.r_bstride, a.r_ld = r.data_ptr(), r_bs, r_ld
+        keep.append(r)
+    elif residual_f32 is not None:
+        r, r_bs, r_ld = _v3(residual_f32, "residual_f32")
+        assert r.dtype == torch.float32 and r.shape[0] == B and r.shape[2] >= N
+        a.residual, a.r_bstride, a.r_ld, a.residual_is_f32 = r.data_ptr(), r_bs, r_ld, 1
+        keep.append(r)
+    elif residual_row is not None:
+        assert residual_row.dtype == x.dtype and residual_row.dim() == 2 and residual_row.stride(1) == 1
+        a.residual, a.r_bstride, a.r_ld = residual_row.data_ptr(), int(residual_row.stride(0)), 0
+        keep.append(residual_row)
+    if ln is not None:
+        a.ln_gamma, a.ln_beta, a.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln_eps
+    if lens is not None:
+        assert lens.dtype == torch.int64
+        a.lens = lens.data_ptr()
+    dot_out = None
+    if dot is not None:
+        dot_out = torch.empty(B, T, device=x.device, dtype=torch.float32)
+        a.dot_w, a.dot_b, a.dot_out = dot[0].data_ptr(), float(dot[1]), dot_out.data_ptr()
+    if out is None and not want_out and (dot is not None or ln is not None) and out_f32 is None and \
+            (impl == IMPL_SIMT or (impl == IMPL_AUTO and B * T < 64)):
+        want_out = True      # the CUDA-core path stages pre-LayerNorm rows in the output buffer
+    if out is None and want_out:
+        ncols = N if vt is None else vt_col0
+        out = torch.empty(B, T, ncols, device=x.device, dtype=x.dtype)
+    if out is not None:
+        o, o_bs, o_ld = _v3(out, "out")
+        assert o.dtype == x.dtype
+        a.out, a.o_bstride, a.o_ld = o.data_ptr(), o_bs, o_ld
+    if out_f32 is not None:
+        f, f_bs, f_ld = _v3(out_f32, "out_f32")
+        assert f.dtype == torch.float32
+        a.out_f32, a.of_bstride, a.of_ld = f.data_ptr(), f_bs, f_ld
+    if vt is not None:
+        assert vt.dtype == x.dtype and vt.dim() == 3 and vt.stride(2) == 1
+        a.vt, a.vt_col0, a.vt_bstride, a.vt_ld = vt.data_ptr(), vt_col0, int(vt.stride(0)), int(vt.stride(1))
+    a.dtype, a.impl = L.dtype_code(x.dtype), impl
+    L.check(L.lib().styler_conv1d_fwd(ctypes.byref(a), L.stream_ptr()), "conv1d")
+    if dot is not None:
+        return out, dot_out
+    return out
+
+
+def attention(qk, vt, lens, n_head=4, *, out=None, impl=IMPL_AUTO):
+    """ctx[B,T,H*64] = softmax(mask(Q K^T)) V ; qk [B,T,2*H*64] (Q pre-scaled), vt [B,H*64,Tpad]."""
+    qk, qk_bs, qk_ld = _v3(qk, "qk")
+    B, T, _ = qk.shape
+    D = n_head * 64
+    if out is None:
+        out = torch.empty(B, T, D, device=qk.device, dtype=qk.dtype)
+    o, o_bs, o_ld = _v3(out, "ctx")
+    L.check(L.lib().styler_attention_fwd(L.ptr(qk), qk_bs, qk_ld, L.ptr(vt), int(vt.stride(0)), int(vt.stride(1)),
+                                         L.ptr(lens), L.ptr(o), o_bs, o_ld, B, T, n_head, L.dtype_code(qk.dtype), impl,
+                                         L.stream_ptr()), "attention")
+    return out
+
+
+def embed_pos(src_seq, emb, pos, dtype):
+    B, Ln = src_seq.shape
+    D = emb.shape[1]
+    out = torch.empty(B, Ln, D, device=src_seq.device, dtype=dtype)
+    L.check(L.lib().styler_embed_pos_fwd(L.ptr(src_seq), L.ptr(emb), emb.shape[0], L.ptr(pos), L.ptr(out), B, Ln, D,
+                                         L.dtype_code(dtype), L.stream_ptr()), "embed_pos")
+    return out
+
+
+def add(a, a2=None, rowvec=None, pos=None, out=None):
+    """out = (a or 0) (+ a2) (+ rowvec[b] broadcast over t) (+ pos[t] fp32 broadcast over b)."""
+    if a is None:
+        o, o_bs, o_ld = _v3(out, "out")
+        B, T, C = o.shape
+        a_bs = a_ld = 0
+    else:
+        a, a_bs, a_ld = _v3(a, "a")
+        B, T, C = a.shape
+        if out is None:
+            out = torch.empty(B, T, C, device=a.device, dtype=a.dtype)
+        o, o_bs, o_ld = _v3(out, "out")
+    a2p, a2_bs, a2_ld = None, 0, 0
+    if a2 is not None:
+        a2, a2_bs, a2_ld = _v3(a2, "a2")
+        a2p = L.ptr(a2)
+    L.check(L.lib().styler_add_fwd(L.ptr(a), a_bs, a_ld, a2p, a2_bs, a2_ld, L.ptr(rowvec),
+                                   int(rowvec.stride(0)) if rowvec is not None else 0, L.ptr(pos), L.ptr(o), o_bs, o_ld,
+                                   B, T, C, L.dtype_code(o.dtype), L.stream_ptr()), "add")
+    return out
+
+
+def cast(x, dtype):
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    L.check(L.lib().styler_cast_fwd(L.ptr(x), L.ptr(out), x.numel(), L.dtype_code(dtype), L.stream_ptr()), "cast")
+    return out
+
+
+def quantize_index(x):
+    x = x.contiguous()
+    idx = torch.empty(x.shape, device=x.device, dtype=torch.int32)
+    L.check(L.lib().styler_quantize_index_fwd(L.ptr(x), L.ptr(idx), x.numel(), L.stream_ptr()), "quantize_index")
+    return idx
+
+
+def onehot_conv(idx, wg, bias, dtype):
+    """idx int32 [B,T]; wg fp32 [KS, nidx, C]; -> [B,T,C]."""
+    B, T = idx.shape
+    KS, nidx, C = wg.shape
+    out = torch.empty(B, T, C, device=idx.device, dtype=dtype)
+    L.check(L.lib().styler_onehot_conv_fwd(L.ptr(idx), L.ptr(wg), L.ptr(bias), L.ptr(out), B, T, C, nidx, KS,
+                                           L.dtype_code(dtype), L.stream_ptr()), "onehot_conv")
+    return out
+
+
+def groupnorm_relu_(x, gamma, beta, ch_per_group=16, eps=1e-5):
+    x3, bs, ld = _v3(x, "x")
+    B, T, C = x3.shape
+    ws = torch.empty(B * (C // ch_per_group) * 2, device=x.device, dtype=torch.float32)
+    L.check(L.lib().styler_groupnorm_relu_fwd(L.ptr(x3), bs, ld, L.ptr(gamma), L.ptr(beta), L.ptr(ws), B, T, C,
+                                              ch_per_group, eps, L.dtype_code(x.dtype), L.stream_ptr()), "groupnorm_relu")
+    return x
+
+
+def mel_calibrator(x, mel_len, src_len, Lmax, out=None):
+    x, x_bs, x_ld = _v3(x, "x")
+    B, Tr, C = x.shape
+    if out is None:
+        out = torch.empty(B, Lmax, C, device=x.device, dtype=x.dtype)
+    o, o_bs, o_ld = _v3(out, "out")
+    L.check(L.lib().styler_mel_calibrator_fwd(L.ptr(x), x_bs, x_ld, L.ptr(mel_len), L.ptr(src_len), L.ptr(o), o_bs, o_ld,
+                                              B, Tr, Lmax, C, L.dtype_code(x.dtype), L.stream_ptr()), "mel_calibrator")
+    return out
+
+
+def bilstm_layer(gx, whh, dtype, out=None):
+    """gx fp32 [B,L,8H]; whh fp32 [2,4H,H] -> [B,L,2H]."""
+    B, Ln, G8 = gx.shape
+    H = G8 // 8
+    assert gx.is_contiguous() and gx.dtype == torch.float32 and whh.is_contiguous()
+    if out is None:
+        out = torch.empty(B, Ln, 2 * H, device=gx.device, dtype=dtype)
+    o, o_bs, o_ld = _v3(out, "out")
+    L.check(L.lib().styler_bilstm_layer_fwd(L.ptr(gx), L.ptr(whh), L.ptr(o), o_bs, o_ld, B, Ln, H, L.dtype_code(dtype),
+                                            L.stream_ptr()), "bilstm_layer")
+    return out
+
+
+def classifier_tail(h, w, b):
+    h, h_bs, h_ld = _v3(h, "h")
+    B, Ln, C = h.shape
+    out = torch.empty(B, 2, device=h.device, dtype=torch.float32)
+    L.check(L.lib().styler_classifier_tail_fwd(L.ptr(h), h_bs, h_ld, L.ptr(w), L.ptr(b), L.ptr(out), B, Ln, C,
+                                               L.dtype_code(h.dtype), L.stream_ptr()), "classifier_tail")
+    return out
+
+
+def duration_round(log_d, log_offset=1.0, d_control=1.0):
+    log_d = log_d.contiguous()
+    out = torch.empty_like(log_d)
+    L.check(L.lib().styler_duration_round_fwd(L.ptr(log_d), L.ptr(out), log_d.numel(), log_offset, d_control,
+                                              L.stream_ptr()), "duration_round")
+    return out
+
+
+def length_regulator(x, duration, Tmax, out=None):
+    """x [B,L,C]; duration int64 or float32 [B,L]; -> (out [B,Tmax,C], mel_len int64 [B], cum int32 [B,L])."""
+    x, x_bs, x_ld = _v3(x, "x")
+    B, Ln, C = x.shape
+    duration = duration.contiguous()
+    if out is None:
+        out = torch.empty(B, Tmax, C, device=x.device, dtype=x.dtype)
+    o, o_bs, o_ld = _v3(out, "out") if Tmax > 0 else (out, 0, C)
+    mel_len = torch.empty(B, device=x.device, dtype=torch.int64)
+    cum = torch.empty(B, Ln, device=x.device, dtype=torch.int32)
+    d64 = duration if duration.dtype == torch.int64 else None
+    d32 = duration if duration.dtype == torch.float32 else None
+    if d64 is None and d32 is None:
+        raise TypeError("duration must be int64 or float32")
+    L.check(L.lib().styler_length_regulator_fwd(L.ptr(x), x_bs, x_ld, L.ptr(d64), L.ptr(d32), L.ptr(o), o_bs, o_ld,
+                                                L.ptr(mel_len), L.ptr(cum), B, Ln, Tmax, C, L.dtype_code(x.dtype),
+                                                L.stream_ptr()), "length_regulator")
+    return out, mel_len, cum
+
+
+def length_regulator_scan(duration):
+    """Integer part only (scan + totals), used to size the output before the expand: -> (mel_len, cum)."""
+    B, Ln = duration.shape
+    dummy = torch.empty(B, Ln, 8, device=duration.device, dtype=torch.float32)
+    _, mel_len, cum = length_regulator(dummy, duration, 0, out=dummy)
+    return mel_len, cum
+
+
+def bucket_embed_sum(text, spk, noise, p_val, e_val, p_scale, e_scale, pitch_bins, energy_bins, pitch_emb, energy_emb,
+                     want_noisy=True, want_idx=False):
+    text, in_bs, in_ld = _v3(text, "text")
+    spk3, s_bs, s_ld = _v3(spk, "spk")
+    assert (s_bs, s_ld) == (in_bs, in_ld), "text/spk/noise must share strides (slices of one expanded buffer)"
+    B, T, C = text.shape
+    out = torch.empty(B, T, C, device=text.device, dtype=text.dtype)
+    out_n = torch.empty_like(out) if want_noisy else None
+    p_idx = torch.empty(B, T, device=text.device, dtype=torch.int32) if want_idx else None
+    e_idx = torch.empty(B, T, device=text.device, dtype=torch.int32) if want_idx else None
+    assert p_val.is_contiguous() and e_val.is_contiguous() and p_val.dtype == torch.float32
+    L.check(L.lib().styler_bucket_embed_sum_fwd(L.ptr(text), L.ptr(spk3), L.ptr(noise) if want_noisy else None, in_bs,
+                                                in_ld, L.ptr(p_val), L.ptr(e_val), p_scale, e_scale, L.ptr(pitch_bins),
+                                                L.ptr(energy_bins), pitch_bins.numel(), L.ptr(pitch_emb),
+                                                L.ptr(energy_emb), L.ptr(out), L.ptr(out_n), int(out.stride(0)),
+                                                int(out.stride(1)), L.ptr(p_idx), L.ptr(e_idx), B, T, C,
+                                                L.dtype_code(text.dtype), L.stream_ptr()), "bucket_embed_sum")
+    return out, out_n, p_idx, e_idx
+
+
+def stft_mel(y, mel_basis):
+    """y fp32 [B,N] -> (mel fp32 [B,n_mels,F], energy fp32 [B,F])."""
+    y = y.contiguous()
+    B, N = y.shape
+    n_mels = mel_basis.shape[0]
+    F = 1 + N // 256
+    mel = torch.empty(B, n_mels, F, device=y.device, dtype=torch.float32)
+    energy = torch.empty(B, F, device=y.device, dtype=torch.float32)
+    band = torch.empty(2 * n_mels, device=y.device, dtype=torch.int32)
+    L.check(L.lib().styler_stft_mel_fwd(L.ptr(y), B, N, L.ptr(mel_basis), n_mels, L.ptr(band), L.ptr(mel), L.ptr(energy),
+                                        L.stream_ptr()), "stft_mel")
+    return mel, energy

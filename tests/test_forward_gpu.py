@@ -1,0 +1,129 @@
+"""End-to-end GPU parity of the drop-in STYLER against the reference's own outputs (tests/golden, produced by
+oracle/make_golden.py from the unmodified reference) and against the CPU oracle at larger sizes.
+
+Tolerances (tensor-normalised max error, |got-ref|.max() / |ref|.max(); north_star: 1e-3 relative on fp32 mels):
+  fp32 mode (CUDA cores)      : 1e-4 everywhere
+  tf32 mode (tcgen05 tf32)    : 1e-3 on the four mels, 5e-3 on predictor outputs
+  bf16 mode (tcgen05 bf16)    : 2e-2 on the mels, 6e-2 on predictor outputs (bf16 has an 8-bit mantissa)
+Integer outputs (mel_len, masks) are bit exact in every mode.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import make_golden as mg
+from oracle import styler_oracle as so
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+TOL = {"fp32": dict(mel=1e-4, pred=1e-4, post=1e-4), "tf32": dict(mel=1e-3, pred=5e-3, post=2e-3),
+       "bf16": dict(mel=2e-2, pred=6e-2, post=3e-2)}
+
+
+def rel(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+def build(case, precision, cuda):
+    from styler_b200 import STYLER
+    sd, batch = mg.build_case(case)
+    model = STYLER(precision=precision)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    return model, sd, batch
+
+
+def run(model, batch, cuda):
+    args, kw = mg.call_kwargs(batch)
+    args = [a.to(cuda) for a in args]
+    kw = {k: (v.to(cuda) if torch.is_tensor(v) else v) for k, v in kw.items()}
+    out = model(*args, **kw)
+    torch.cuda.synchronize()
+    return mg.flatten_outputs(out)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("case", sorted(mg.CASES))
+def test_forward_vs_reference_golden(cuda, case, precision):
+    gold = torch.load(os.path.join(GOLD, case + ".pt"))
+    model, sd, batch = build(case, precision, cuda)
+    assert mg.sd_checksum(sd) == gold["_weights_sha256"], "seeded weight generator drifted"
+    got = run(model, batch, cuda)
+    tol = TOL[precision]
+    assert torch.equal(got["mel_len"].cpu(), gold["mel_len"])
+    assert torch.equal(got["src_mask"].cpu(), gold["src_mask"]) and torch.equal(got["mel_mask"].cpu(), gold["mel_mask"])
+    errs = {}
+    for k in ("mel", "mel_noisy", "mel_postnet", "mel_postnet_noisy"):
+        errs[k] = rel(got[k], gold[k])
+        assert errs[k] < tol["mel"], (case, precision, k, errs[k])
+    for k in ("log_d", "p_pred", "e_pred"):
+        errs[k] = rel(got[k], gold[k])
+        assert errs[k] < tol["pred"], (case, precision, k, errs[k])
+    for k in ("aug_d", "aug_p", "aug_e"):
+        errs[k] = rel(got[k], gold[k])
+        assert errs[k] < tol["post"], (case, precision, k, errs[k])
+    sm = model.style_modeling
+    assert rel(sm.text_encoding, gold["i_text_encoding"]) < tol["mel"]
+    assert rel(sm.duration_encoding, gold["i_duration_encoding"]) < tol["pred"]
+    assert rel(sm.noise_encoding, gold["i_noise_encoding"]) < tol["pred"]
+    print("\n%s/%s " % (case, precision) + " ".join("%s=%.1e" % kv for kv in errs.items()))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_forward_config3_shape_vs_oracle(cuda, precision):
+    """BASELINE config 3 geometry (L=128 -> T=1024, teacher-forced 8 frames/phoneme) at B=4 against the CPU oracle,
+    plus size-independent properties: padded mel frames equal mel_linear.bias (SURVEY 8(a) trap 2), FFT-block outputs
+    are exactly zero on padded rows, and two runs are bitwise identical."""
+    from styler_b200 import STYLER
+    sd = so.make_state_dict(0)
+    batch = so.make_inputs(B=4, L=128, seed=77, ragged=True, d_mode="const", frames=8)
+    model = STYLER(precision=precision)
+    model.load_state_dict(sd)
+    model = model.to(cuda).eval()
+    got = run(model, batch, cuda)
+    got2 = run(model, batch, cuda)
+    for k in ("mel", "mel_postnet_noisy", "p_pred"):
+        assert torch.equal(got[k], got2[k]), "non-deterministic " + k
+    args, kw = mg.call_kwargs(batch)
+    with torch.no_grad():
+        ref = mg.flatten_outputs(so.styler_forward(sd, *args, **kw))
+    tol = TOL[precision]
+    for k in ("mel", "mel_noisy", "mel_postnet", "mel_postnet_noisy"):
+        assert rel(got[k], ref[k]) < tol["mel"], (k, rel(got[k], ref[k]))
+    for k in ("log_d", "p_pred", "e_pred"):
+        assert rel(got[k], ref[k]) < tol["pred"], (k, rel(got[k], ref[k]))
+    pad = ref["mel_mask"]
+    assert pad.any()
+    bias = sd["mel_linear.bias"]
+    padded_rows = got["mel"].cpu()[pad]
+    assert (padded_rows - bias).abs().max() < (1e-6 if precision != "bf16" else 1e-6), "padded mel frames must equal mel_linear.bias"
+    assert torch.equal(got["mel_len"].cpu(), ref["mel_len"])
+
+
+def test_decode_entry_point(cuda):
+    """STYLER.decode(x, mel_mask) (styler.py:29-37), called directly by synthesize.py:172,202,313."""
+    from styler_b200 import STYLER
+    sd = so.make_state_dict(0)
+    model = STYLER(precision="fp32")
+    model.load_state_dict(sd)
+    model = model.to(cuda).eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 70, 256, generator=g)
+    lens = torch.tensor([70, 33])
+    mask = so.mask_from_lengths(lens, 70)
+    x = x.masked_fill(mask.unsqueeze(-1), 0)
+    with torch.no_grad():
+        ref_mel, ref_post = so.decode(sd, x, mask)
+    mel, post = model.decode(x.to(cuda), mask.to(cuda))
+    assert rel(mel, ref_mel) < 1e-4 and rel(post, ref_post) < 1e-4
+
+
+def test_no_cpu_fallback():
+    """The product path must refuse to run without CUDA tensors / device."""
+    from styler_b200 import STYLER
+    m = STYLER().eval()
+    with pytest.raises(RuntimeError):
+        m(*[torch.zeros(1, 4, dtype=torch.long)] * 7)

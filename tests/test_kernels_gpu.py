@@ -1,0 +1,311 @@
+"""GPU parity tests of every C-ABI kernel against a CPU fp32 restatement of the same op (oracle functions where the
+op exists in the reference, plain torch otherwise).  Integer / index outputs are compared bit-exactly."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import styler_oracle as so
+from oracle import stft_oracle
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {0: lambda v: v, 1: torch.relu, 2: torch.tanh}
+
+
+def _ops():
+    from styler_b200 import ops
+    return ops
+
+
+def rel_err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+def conv_ref(x, w, bias, pad, act=0, residual=None, ln=None, act2=0, lens=None, dot=None):
+    """fp32 CPU statement of the styler_conv1d_fwd contract; x [B,T,Cin], w [KS,N,Cin]."""
+    y = F.conv1d(x.transpose(1, 2), w.permute(1, 2, 0).contiguous(), bias, padding=pad).transpose(1, 2)
+    y = ACTS[act](y)
+    if residual is not None:
+        y = y + residual
+    if ln is not None:
+        y = F.layer_norm(y, (y.shape[-1],), ln[0], ln[1], 1e-5)
+    y = ACTS[act2](y)
+    d = None
+    if dot is not None:
+        d = y @ dot[0] + dot[1]
+    if lens is not None:
+        m = so.mask_from_lengths(lens, y.shape[1])
+        y = y.masked_fill(m.unsqueeze(-1), 0)
+        if d is not None:
+            d = d.masked_fill(m, 0)
+    return y, d
+
+
+CONV_CASES = [
+    # name,               B, T,   Cin,  N,    KS, kw
+    ("linear_bias",       2, 200, 256,  256,  1, dict()),
+    ("ffn1_k9_relu",      2, 300, 256,  1024, 9, dict(act=1)),
+    ("ffn2_res_ln_mask",  3, 130, 1024, 256,  1, dict(res=True, ln=True, lens=True)),
+    ("pred_k3_relu_ln_dot", 2, 257, 256, 256, 3, dict(act=1, ln=True, lens=True, dot=True)),
+    ("postnet_in_k5_tanh", 2, 140, 80,  512,  5, dict(act=2)),
+    ("postnet_out_k5_res_f32", 2, 140, 512, 80, 5, dict(res=True, f32=True)),
+    ("qkv_vt_split",      2, 150, 256,  768,  1, dict(vt=True)),
+    ("lstm_proj_k160",    2, 128, 160,  640,  1, dict(f32only=True)),
+    ("cls_ln_relu",       2, 64,  128,  256,  1, dict(ln=True, act2=1)),
+    ("audio_k5_320",      2, 200, 320,  320,  5, dict()),
+    ("row_broadcast_res", 2, 96,  128,  256,  1, dict(act=1, res_row=True)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_conv1d(cuda, case, dtype, impl):
+    ops = _ops()
+    name, B, T, Cin, N, KS, kw = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(B, T, Cin, generator=g)
+    w = (torch.rand(KS, N, Cin, generator=g) * 2 - 1) / math.sqrt(Cin * KS)
+    bias = torch.randn(N, generator=g) * 0.1
+    xq, wq = x.to(dtype).float(), w.to(dtype).float()          # operands exactly as the kernel sees them
+    res = torch.randn(B, T, N, generator=g) if kw.get("res") else None
+    res_row = torch.randn(B, N, generator=g) if kw.get("res_row") else None
+    ln = (1 + 0.1 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g)) if kw.get("ln") else None
+    lens = torch.tensor([T, max(1, T // 2), max(1, T - 7)][:B], dtype=torch.int64) if kw.get("lens") else None
+    dot = ((torch.rand(N, generator=g) - 0.5) * 0.2, 0.3) if kw.get("dot") else None
+    resq = res.to(dtype).float() if res is not None else (res_row.to(dtype).float().unsqueeze(1) if res_row is not None else None)
+    pad = (KS - 1) // 2
+    ref, ref_dot = conv_ref(xq, wq, bias, pad, kw.get("act", 0), resq, ln, kw.get("act2", 0), lens, dot)
+
+    dev = cuda
+    xd, wd = x.to(dev, dtype), w.to(dev, dtype)
+    args = dict(pad=pad, act=kw.get("act", 0), act2=kw.get("act2", 0),
+                impl=ops.IMPL_SIMT if impl == "simt" else ops.IMPL_TC)
+    if res is not None:
+        args["residual"] = res.to(dev, dtype)
+    if res_row is not None:
+        args["residual_row"] = res_row.to(dev, dtype)
+    if ln is not None:
+        args["ln"] = (ln[0].to(dev), ln[1].to(dev))
+    if lens is not None:
+        args["lens"] = lens.to(dev)
+    if dot is not None:
+        args["dot"] = (dot[0].to(dev), dot[1])
+    out_f32 = torch.zeros(B, T, N, device=dev) if (kw.get("f32") or kw.get("f32only")) else None
+    if out_f32 is not None:
+        args["out_f32"] = out_f32
+    vt = None
+    if kw.get("vt"):
+        Tp = (T + 63) // 64 * 64
+        vt = torch.zeros(B, 256, Tp, device=dev, dtype=dtype)
+        args.update(vt=vt, vt_col0=512)
+    if kw.get("f32only"):
+        args["want_out"] = False
+    got = ops.conv1d(xd, wd, bias.to(dev), **args)
+    torch.cuda.synchronize()
+    got_dot = None
+    if dot is not None:
+        got, got_dot = got
+    # tolerance: operands are identical, so only accumulation order (and tf32 operand rounding) differs
+    tol_acc = 2e-3 if (dtype == torch.float32 and impl == "tc") else 2e-5
+    tol_out = tol_acc + (8e-3 if dtype == torch.bfloat16 else 0.0)    # bf16 storage of the result
+    if kw.get("ln") and dtype == torch.bfloat16 and impl == "simt":
+        tol_out += 2e-2                                                # simt stages pre-LN rows in bf16
+    if vt is not None:
+        assert rel_err(got, ref[..., :512]) < tol_out
+        assert rel_err(vt[:, :, :T].transpose(1, 2), ref[..., 512:]) < tol_out
+    elif not kw.get("f32only"):
+        assert rel_err(got, ref) < tol_out, name
+    if out_f32 is not None:
+        assert rel_err(out_f32, ref) < (tol_out if (kw.get("ln") and impl == "simt") else tol_acc)
+    if got_dot is not None:
+        assert rel_err(got_dot, ref_dot) < tol_out + 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("T", [128, 200, 520])
+def test_attention(cuda, dtype, impl, T):
+    ops = _ops()
+    B, H = 3, 4
+    g = torch.Generator().manual_seed(T)
+    qk = torch.randn(B, T, 512, generator=g)
+    v = torch.randn(B, T, 256, generator=g)
+    lens = torch.tensor([T, max(1, T // 3), max(1, T - 5)], dtype=torch.int64)
+    qkq, vq = qk.to(dtype).float(), v.to(dtype).float()
+    q = qkq[..., :256].view(B, T, H, 64).permute(0, 2, 1, 3)
+    k = qkq[..., 256:].view(B, T, H, 64).permute(0, 2, 1, 3)
+    vv = vq.view(B, T, H, 64).permute(0, 2, 1, 3)
+    s = q @ k.transpose(-1, -2)
+    s = s.masked_fill(so.mask_from_lengths(lens, T)[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vv).permute(0, 2, 1, 3).reshape(B, T, 256)
+    Tp = (T + 63) // 64 * 64
+    vt = torch.zeros(B, 256, Tp, dtype=dtype)
+    vt[:, :, :T] = v.to(dtype).transpose(1, 2)
+    got = ops.attention(qk.to(cuda, dtype), vt.to(cuda), lens.to(cuda), H,
+                        impl=ops.IMPL_SIMT if impl == "simt" else ops.IMPL_TC)
+    torch.cuda.synchronize()
+    tol = {("simt", torch.float32): 2e-5, ("simt", torch.bfloat16): 8e-3, ("tc", torch.float32): 3e-3,
+           ("tc", torch.bfloat16): 1.5e-2}[(impl, dtype)]
+    assert rel_err(got, ref) < tol
+
+
+def test_embed_add_cast(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    seq = torch.randint(0, 152, (3, 37), generator=g)
+    emb, pos = torch.randn(152, 256, generator=g), torch.randn(37, 256, generator=g)
+    got = ops.embed_pos(seq.to(cuda), emb.to(cuda), pos.to(cuda), torch.float32)
+    assert torch.equal(got.cpu(), emb[seq] + pos.unsqueeze(0))
+    a, a2, rv = torch.randn(3, 37, 256, generator=g), torch.randn(3, 37, 256, generator=g), torch.randn(3, 256, generator=g)
+    got = ops.add(a.to(cuda), a2.to(cuda), rv.to(cuda), pos.to(cuda))
+    assert torch.allclose(got.cpu(), ((a + rv.unsqueeze(1)) + pos.unsqueeze(0)) + a2, atol=1e-6)
+    assert torch.equal(ops.cast(a.to(cuda), torch.bfloat16).cpu(), a.to(torch.bfloat16))
+
+
+def test_quantize_index_bit_exact(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(4, 1000, generator=g)
+    x[0, :300] = 0.0
+    x[1, :255] = (torch.arange(255) + 0.5) / 255.0          # exact .5 ties -> half-to-even
+    x[2, 0], x[2, 1] = 1.0, -0.25
+    got = ops.quantize_index(x.to(cuda)).cpu().long()
+    ref = so.quantize_index(x.clamp(max=1.0))
+    bad = (got != ref).nonzero()
+    assert bad.numel() == 0, (bad[:8], x[got != ref][:8], got[got != ref][:8], ref[got != ref][:8])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_onehot_conv_groupnorm(cuda, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(7)
+    B, T, C = 2, 77, 320
+    idx = torch.randint(0, 257, (B, T), generator=g)
+    w = torch.randn(C, 257, 5, generator=g) * 0.1
+    bias = torch.randn(C, generator=g) * 0.1
+    ref = F.conv1d(F.one_hot(idx, 257).float().transpose(1, 2), w, bias, padding=2)
+    wg = w.permute(2, 1, 0).contiguous()
+    got = ops.onehot_conv(idx.int().to(cuda), wg.to(cuda), bias.to(cuda), dtype)
+    assert rel_err(got.transpose(1, 2), ref) < (1e-5 if dtype == torch.float32 else 8e-3)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    xin = got.clone()
+    ref2 = F.relu(F.group_norm(xin.float().cpu().transpose(1, 2), C // 16, gamma, beta, 1e-5)).transpose(1, 2)
+    ops.groupnorm_relu_(xin, gamma.to(cuda), beta.to(cuda))
+    assert rel_err(xin, ref2) < (2e-5 if dtype == torch.float32 else 8e-3)
+
+
+def test_mel_calibrator(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    B, Tr, C, Lm = 5, 97, 64, 40
+    x = torch.randn(B, Tr, C, generator=g)
+    mel_len = torch.tensor([97, 40, 13, 96, 41])
+    src_len = torch.tensor([40, 40, 40, 7, 39])            # compress, equal, expand, compress, compress(1.05x)
+    ref = so.mel_calibrator(x, mel_len, src_len)
+    got = ops.mel_calibrator(x.to(cuda), mel_len.to(cuda), src_len.to(cuda), Lm).cpu()
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("H,Cin", [(80, 256), (64, 320)])
+def test_bilstm(cuda, H, Cin):
+    ops = _ops()
+    sd = {k: v for k, v in so.make_state_dict(0).items() if "lstm_1." in k or "lstm_2." in k}
+    p = "style_modeling.style_encoder.audio_encoder.lstm_%d." % (1 if H == 80 else 2)
+    g = torch.Generator().manual_seed(11)
+    B, Ln = 3, 50
+    x = torch.randn(B, Ln, Cin, generator=g)
+    ref = so.bilstm2(sd, p, x)
+    cur = x.to(cuda)
+    for layer in range(2):
+        wih = torch.cat([sd[p + "weight_ih_l%d" % layer], sd[p + "weight_ih_l%d_reverse" % layer]], 0)
+        b = torch.cat([sd[p + "bias_ih_l%d" % layer] + sd[p + "bias_hh_l%d" % layer],
+                       sd[p + "bias_ih_l%d_reverse" % layer] + sd[p + "bias_hh_l%d_reverse" % layer]], 0)
+        whh = torch.stack([sd[p + "weight_hh_l%d" % layer], sd[p + "weight_hh_l%d_reverse" % layer]], 0)
+        gx = torch.empty(B, Ln, 8 * H, device=cuda)
+        ops.conv1d(cur, wih.unsqueeze(0).contiguous().to(cuda), b.to(cuda), out_f32=gx, want_out=False, impl=ops.IMPL_SIMT)
+        cur = ops.bilstm_layer(gx, whh.contiguous().to(cuda), torch.float32)
+    assert rel_err(cur, ref) < 2e-5
+
+
+def test_classifier_tail_duration(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    h = torch.randn(3, 21, 256, generator=g)
+    w, b = torch.randn(2, 256, generator=g) * 0.1, torch.randn(2, generator=g)
+    ref = F.log_softmax(F.linear(h, w, b), -1).mean(1)
+    got = ops.classifier_tail(h.to(cuda), w.to(cuda), b.to(cuda)).cpu()
+    assert torch.allclose(got, ref, atol=1e-5)
+    log_d = torch.randn(4, 33, generator=g) * 1.5
+    for ctl in (1.0, 1.3):
+        got = ops.duration_round(log_d.to(cuda), 1.0, ctl).cpu()
+        ref = so.duration_from_log(log_d, ctl)
+        assert (got != ref).float().mean() < 0.01           # exp() may differ by 1 ulp exactly at a .5 tie
+        assert (got - ref).abs().max() <= ctl + 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("dur_kind", ["int64", "float32"])
+def test_length_regulator_bit_exact(cuda, dtype, dur_kind):
+    ops = _ops()
+    g = torch.Generator().manual_seed(17)
+    B, Ln, C = 4, 33, 1280
+    x = torch.randn(B, Ln, C, generator=g).to(dtype)
+    if dur_kind == "int64":
+        dur = torch.randint(0, 9, (B, Ln), generator=g)
+        dur[1] = 0                                            # an utterance that expands to nothing
+    else:
+        dur = torch.rand(B, Ln, generator=g) * 6.0            # 2.6 -> 2 (truncation, modules.py:415-416)
+    for Tmax in (None, 50, 400):
+        ref, ref_len = so.length_regulator(x.float(), dur, Tmax)
+        T = ref.shape[1]
+        got, mel_len, cum = ops.length_regulator(x.to(cuda), dur.to(cuda), T)
+        assert torch.equal(mel_len.cpu(), ref_len)
+        reps = dur.long() if dur_kind == "int64" else dur.double().trunc().long()
+        assert torch.equal(cum.cpu().long(), reps.cumsum(1))
+        assert torch.equal(got.float().cpu(), ref)            # pure copy: bit exact in any dtype
+
+
+def test_bucket_embed_sum(cuda):
+    ops = _ops()
+    sd = so.make_state_dict(0)
+    P = "style_modeling."
+    g = torch.Generator().manual_seed(19)
+    B, T, C = 2, 45, 256
+    enc = torch.randn(B, T, 1280, generator=g)
+    p = torch.rand(B, T, generator=g) * 900
+    e = torch.rand(B, T, generator=g) * 600
+    p[0, :5] = sd[P + "pitch_bins"][[0, 1, 100, 253, 254]]     # exactly on a boundary: bins[i-1] < x <= bins[i]
+    e[0, :3] = torch.tensor([0.0, 0.1, 1e4])
+    pi, ei = torch.bucketize(p, sd[P + "pitch_bins"]), torch.bucketize(e, sd[P + "energy_bins"])
+    text, spk, noise = enc[..., :256], enc[..., 512:768], enc[..., 1024:]
+    ref = text + F.embedding(pi, sd[P + "pitch_embedding.weight"]) + spk + F.embedding(ei, sd[P + "energy_embedding.weight"])
+    encd = enc.to(cuda)
+    out, out_n, gpi, gei = ops.bucket_embed_sum(encd[..., :256], encd[..., 512:768], encd[..., 1024:], p.to(cuda), e.to(cuda),
+                                                1.0, 1.0, sd[P + "pitch_bins"].to(cuda), sd[P + "energy_bins"].to(cuda),
+                                                sd[P + "pitch_embedding.weight"].to(cuda),
+                                                sd[P + "energy_embedding.weight"].to(cuda), want_idx=True)
+    assert torch.equal(gpi.cpu().long(), pi) and torch.equal(gei.cpu().long(), ei)
+    assert torch.equal(out.cpu(), ref)
+    assert torch.allclose(out_n.cpu(), ref + noise, atol=1e-6)
+
+
+def test_stft_mel(cuda):
+    ops = _ops()
+    gold = torch.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "stft_b3_n6000.pt"))
+    g = torch.Generator().manual_seed(gold["seed"])
+    y = (torch.rand(*gold["shape"], generator=g) * 2 - 1) * 0.5
+    basis = torch.from_numpy(stft_oracle.slaney_mel_basis(22050, 1024, 80, 0.0, 8000.0))
+    mel, energy = ops.stft_mel(y.to(cuda), basis.to(cuda))
+    assert (mel.cpu() - gold["mel"]).abs().max() < 1e-3
+    assert rel_err(energy, gold["energy"]) < 1e-4
+    # a longer, config-4 shaped utterance against the oracle
+    y2 = (torch.rand(2, 88200, generator=g) * 2 - 1) * 0.5
+    m_ref, e_ref = stft_oracle.mel_spectrogram(y2)
+    m2, e2 = ops.stft_mel(y2.to(cuda), basis.to(cuda))
+    assert m2.shape == (2, 80, 345)
+    assert (m2.cpu() - m_ref).abs().max() < 1e-3 and rel_err(e2, e_ref) < 1e-4
