@@ -270,11 +270,11 @@ class STYLER(nn.Module):
 
     def _engine_for(self, like=None):
         dev = self.mel_linear.weight.device
+        if self.training:
+            raise RuntimeError("styler_b200.STYLER implements the eval-mode forward only; call .eval()")
         if dev.type != "cuda":
             raise RuntimeError("styler_b200.STYLER runs only on a CUDA (sm_100a) device; call .cuda() first -- "
                                "there is no CPU fallback")
-        if self.training:
-            raise RuntimeError("styler_b200.STYLER implements the eval-mode forward only; call .eval()")
         if self._engine is None or self._engine.device != dev or self._engine.precision != self.precision:
             with torch.no_grad():
                 object.__setattr__(self, "_engine", Engine(self.state_dict(), dev, self.precision))
