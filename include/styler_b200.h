@@ -144,6 +144,10 @@ int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_b
                         int32_t* band_ws /* [2*n_mels] workspace: non-zero band of each filter row */, float* mel,
                         float* energy, void* stream);
 
+/* ---- Debug/tuning hook: when a device buffer of capacity_ctas*8 int64 is set, every tcgen05 conv launch with at most
+ * capacity_ctas CTAs writes 8 clock64() phase stamps per CTA into it (tools/phase_timing.py); NULL disables. */
+int styler_debug_set_phase_buffer(int64_t* buf, int32_t capacity_ctas);
+
 #ifdef __cplusplus
 }
 #endif

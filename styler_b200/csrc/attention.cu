@@ -69,6 +69,12 @@ constexpr int kQ = 128;    // queries per CTA
 constexpr int kKV = 128;   // keys per step
 constexpr int kThreadsTc = 192;
 
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2, flush-to-zero; inputs are <= 0 here
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <typename T> struct AttnCfg {
   static constexpr int es = sizeof(T);
   static constexpr int bke = 128 / es;              // elements per 128-byte slice
@@ -80,7 +86,7 @@ template <typename T> struct AttnCfg {
   static constexpr int p_bytes = pv_slices * kQ * 128;
   static constexpr int kv_stages = es == 2 ? 2 : 1;
   static constexpr int umma_k = 32 / es;
-  static constexpr size_t smem = q_bytes + kv_stages * (k_bytes + v_bytes) + p_bytes + 1024 + 256;
+  static constexpr size_t smem = q_bytes + kv_stages * (k_bytes + v_bytes) + p_bytes + 512 + 256;  // bf16: 2 CTAs/SM
 };
 
 template <typename T>
@@ -104,6 +110,10 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
   uint64_t* p_ready = bars + 6;
   uint64_t* o_full = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  if (threadIdx.x == 0 && static_cast<size_t>(reinterpret_cast<uint8_t*>(tmem_slot + 1) - smem_raw) > C::smem) {
+    printf("styler_b200: attention smem carve-up overflows the allocation (base misaligned)\n");
+    __trap();
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % q_tiles;
@@ -200,16 +210,22 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kbase = j * kKV;
+      const bool full_tile = kbase + kKV <= len;           // only the last key tile needs the padding mask
       float mx = m_run;
       for (int c = 0; c < kKV; c += 16) {
         uint32_t raw[16];
         tmem_ld16(tmem_S + lane_off + c, raw);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (kbase + c + i < len) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (kbase + c + i < len) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        }
       }
-      const float alpha = m_run == -INFINITY ? 0.f : exp2f((m_run - mx) * kLog2e);
+      const float alpha = m_run == -INFINITY ? 0.f : fast_exp2((m_run - mx) * kLog2e);
       l_run *= alpha;
 #pragma unroll
       for (int i = 0; i < 64; ++i) o[i] *= alpha;
@@ -219,11 +235,19 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
         tmem_ld16(tmem_S + lane_off + c, raw);
         tmem_ld_wait();
         float pv[16];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e = kbase + c + i < len ? exp2f(fmaf(__uint_as_float(raw[i]), kLog2e, -mxl)) : 0.f;
-          pv[i] = e;
-          l_run += e;
+          for (int i = 0; i < 16; ++i) {
+            pv[i] = fast_exp2(fmaf(__uint_as_float(raw[i]), kLog2e, -mxl));
+            l_run += pv[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = kbase + c + i < len ? fast_exp2(fmaf(__uint_as_float(raw[i]), kLog2e, -mxl)) : 0.f;
+            pv[i] = e;
+            l_run += e;
+          }
         }
         // P[r][c..c+15] -> K-major 128B-swizzled smem (A operand of the PV MMA)
         const int byte0 = c * C::es;                       // byte offset of key c within the row

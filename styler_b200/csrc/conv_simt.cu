@@ -163,3 +163,9 @@ extern "C" int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream) {
   SB_REQUIRE(impl == STYLER_IMPL_SIMT, "conv1d: bad impl %d", a->impl);
   return conv1d_simt(*a, s);
 }
+
+// Debug/tuning hook (tools/phase_timing.py): per-CTA clock64() phase stamps of the tcgen05 conv kernel; NULL disables.
+extern "C" int styler_debug_set_phase_buffer(int64_t* buf, int32_t capacity_ctas) {
+  sb::set_phase_buffer(reinterpret_cast<long long*>(buf), capacity_ctas);
+  return 0;
+}

@@ -32,7 +32,14 @@ constexpr int kBM = 128;
 constexpr int kAStageBytes = kBM * 128;
 constexpr int kThreads = 192;
 
+// Optional per-CTA phase timestamps (tools/phase_timing.py): 8 x int64 per CTA written with clock64():
+// [0] kernel entry  [1] after TMEM alloc + setup sync  [2] MMA thread: first stage full  [3] MMA thread: all issued
+// [4] epilogue: tmem_full observed  [5] epilogue: LN pass 1 done  [6] epilogue done  [7] before exit
+long long* g_phase_buf = nullptr;
+int g_phase_cap = 0;
+
 struct EpiParams {
+  long long* dbg;
   const float* bias;
   int act, act2;
   const void* residual; long long r_bstride; int r_ld; int res_f32;
@@ -78,8 +85,11 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_par = reinterpret_cast<float*>(smem + stages * stage_bytes + 256);   // [4][256]: bias, gamma, beta, dot_w
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = ep.dbg != nullptr ? ep.dbg + static_cast<long long>(blockIdx.x) * 8 : nullptr;
+  if (dbg != nullptr && threadIdx.x == 0) dbg[0] = clock64();
   const int nt = blockIdx.x % n_tiles, mt = blockIdx.x / n_tiles;
   const int b = mt / tiles_per_utt, t0 = (mt % tiles_per_utt) * kBM;
   const int n0 = nt * BN;
@@ -98,6 +108,7 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg != nullptr && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -121,6 +132,7 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
         const int s = kb % stages;
         const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&full[s], ph);
+        if (dbg != nullptr && kb == 0) dbg[2] = clock64();
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t b_addr = a_addr + kAStageBytes;
@@ -132,6 +144,7 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
+      if (dbg != nullptr) dbg[3] = clock64();
     }
     __syncwarp();
   } else {
@@ -143,10 +156,11 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool masked = ep.lens != nullptr && row_ok && t >= static_cast<int>(ep.lens[b]);
     const bool has_ln = ep.ln_gamma != nullptr;
+    const bool has_res = ep.residual != nullptr;
     const bool to_vt = ep.vt != nullptr && n0 >= ep.vt_col0;
     const T* res_row = nullptr;
     const float* res_row_f = nullptr;
-    if (ep.residual != nullptr) {
+    if (has_res) {
       const long long off = b * ep.r_bstride + static_cast<long long>(t) * ep.r_ld + n0;
       if (ep.res_f32) res_row_f = static_cast<const float*>(ep.residual) + off;
       else res_row = static_cast<const T*>(ep.residual) + off;
@@ -161,39 +175,80 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
                              static_cast<long long>(n0 - ep.vt_col0) * ep.vt_ld + t
                        : nullptr;
 
+    // Per-column parameters of this N tile staged in smem once per CTA (while the mainloop runs): reading them with
+    // 16 dependent global loads per chunk was the dominant epilogue cost.
+    {
+      const int te = threadIdx.x - 64;
+      for (int i = te; i < BN; i += 128) {
+        s_par[i] = ep.bias != nullptr ? ep.bias[n0 + i] : 0.f;
+        s_par[256 + i] = has_ln ? ep.ln_gamma[n0 + i] : 1.f;
+        s_par[512 + i] = has_ln ? ep.ln_beta[n0 + i] : 0.f;
+        s_par[768 + i] = ep.dot_w != nullptr ? ep.dot_w[n0 + i] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const float* s_bias = s_par;
+    const float* s_gamma = s_par + 256;
+    const float* s_beta = s_par + 512;
+    const float* s_dot = s_par + 768;
+
+    auto load_res = [&](int c, float (&rr)[16]) {       // residual columns c..c+15 of this thread's row
+      if (res_row_f != nullptr) load16(res_row_f + c, rr); else load16(res_row + c, rr);
+    };
+    auto act_inplace = [&](float (&v)[16], int act) {
+      if (act == STYLER_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if (act == STYLER_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+      }
+    };
+
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
 
     float mean = 0.f, rstd = 1.f;
     if (has_ln) {
-      // pass 1: v = act(acc + bias) + residual, parked back in TMEM; shifted sums for mean/variance
+      // pass 1: v = act(acc + bias) + residual, parked back in TMEM; shifted sums for mean/variance.
+      // Two 16-column chunks per iteration so TMEM and residual loads of both are in flight together.
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + c, raw);
+      for (int c = 0; c < BN; c += 32) {
+        const bool two = c + 16 < BN;
+        uint32_t ra[16], rb[16];
+        float xa[16], xb[16];
+        tmem_ld16(taddr + c, ra);
+        if (two) tmem_ld16(taddr + c + 16, rb);
+        if (has_res && row_ok) { load_res(c, xa); if (two) load_res(c + 16, xb); }
         tmem_ld_wait();
-        float v[16];
+        {
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = __uint_as_float(raw[i]);
-          if (ep.bias != nullptr) x += __ldg(ep.bias + n0 + c + i);
-          v[i] = apply_act(x, ep.act);
-        }
-        if ((res_row != nullptr || res_row_f != nullptr) && row_ok) {
-          float rr[16];
-          if (res_row_f != nullptr) load16(res_row_f + c, rr); else load16(res_row + c, rr);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + s_bias[c + i];
+          act_inplace(v, ep.act);
+          if (has_res && row_ok) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += rr[i];
-        }
-        if (c == 0) shift = v[0];
+            for (int i = 0; i < 16; ++i) v[i] += xa[i];
+          }
+          if (c == 0) shift = v[0];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float d = v[i] - shift;
-          s1 += d;
-          s2 += d * d;
-          raw[i] = __float_as_uint(v[i]);
+          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1 += d; s2 += d * d; ra[i] = __float_as_uint(v[i]); }
+          tmem_st16(taddr + c, ra);
         }
-        tmem_st16(taddr + c, raw);
+        if (two) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + s_bias[c + 16 + i];
+          act_inplace(v, ep.act);
+          if (has_res && row_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += xb[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1 += d; s2 += d * d; rb[i] = __float_as_uint(v[i]); }
+          tmem_st16(taddr + c + 16, rb);
+        }
       }
       tmem_st_wait();
       const float inv_n = 1.0f / static_cast<float>(BN);
@@ -202,41 +257,14 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
       const float var = fmaxf(s2 * inv_n - dm * dm, 0.f);
       rstd = rsqrtf(var + ep.ln_eps);
     }
+    if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
 
     float dot = 0.f;
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t raw[16];
-      tmem_ld16(taddr + c, raw);
-      tmem_ld_wait();
-      float v[16];
-      if (has_ln) {
+    const bool has_dot = ep.dot_w != nullptr;
+    auto finish_chunk = [&](int c, float (&v)[16]) {   // v = final values of columns c..c+15
+      if (has_dot) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float y = (__uint_as_float(raw[i]) - mean) * rstd * __ldg(ep.ln_gamma + n0 + c + i) +
-                          __ldg(ep.ln_beta + n0 + c + i);
-          v[i] = apply_act(y, ep.act2);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = __uint_as_float(raw[i]);
-          if (ep.bias != nullptr) x += __ldg(ep.bias + n0 + c + i);
-          v[i] = apply_act(x, ep.act);
-        }
-        if ((res_row != nullptr || res_row_f != nullptr) && row_ok) {
-          float rr[16];
-          if (res_row_f != nullptr) load16(res_row_f + c, rr); else load16(res_row + c, rr);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += rr[i];
-        }
-        if (ep.act2 != STYLER_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], ep.act2);
-        }
-      }
-      if (ep.dot_w != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) dot += v[i] * __ldg(ep.dot_w + n0 + c + i);
+        for (int i = 0; i < 16; ++i) dot = fmaf(v[i], s_dot[c + i], dot);
       }
       if (masked) {
 #pragma unroll
@@ -246,23 +274,67 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
         if (to_vt) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) DT<T>::st(vt_base + static_cast<long long>(c + i) * ep.vt_ld, v[i]);
-        } else if (out_row != nullptr) {
-          store16(out_row + c, v);
-        }
-        if (of_row != nullptr && !to_vt) {
+        } else {
+          if (out_row != nullptr) store16(out_row + c, v);
+          if (of_row != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(of_row + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(of_row + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
         }
+      }
+    };
+    for (int c = 0; c < BN; c += 32) {
+      const bool two = c + 16 < BN;
+      uint32_t ra[16], rb[16];
+      float xa[16], xb[16];
+      tmem_ld16(taddr + c, ra);
+      if (two) tmem_ld16(taddr + c + 16, rb);
+      const bool need_res = has_res && !has_ln && row_ok;
+      if (need_res) { load_res(c, xa); if (two) load_res(c + 16, xb); }
+      tmem_ld_wait();
+      float v[16];
+      if (has_ln) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(ra[i]) - mean) * rstd * s_gamma[c + i] + s_beta[c + i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + s_bias[c + i];
+        act_inplace(v, ep.act);
+        if (need_res) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += xa[i];
+        }
+      }
+      act_inplace(v, ep.act2);
+      finish_chunk(c, v);
+      if (two) {
+        if (has_ln) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] = (__uint_as_float(rb[i]) - mean) * rstd * s_gamma[c + 16 + i] + s_beta[c + 16 + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + s_bias[c + 16 + i];
+          act_inplace(v, ep.act);
+          if (need_res) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += xb[i];
+          }
+        }
+        act_inplace(v, ep.act2);
+        finish_chunk(c + 16, v);
       }
     }
     if (ep.dot_out != nullptr && row_ok)
       ep.dot_out[static_cast<long long>(b) * Tlen + t] = masked ? 0.f : dot + ep.dot_b;
+    if (dbg != nullptr && threadIdx.x == 64) dbg[6] = clock64();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (dbg != nullptr && threadIdx.x == 0) dbg[7] = clock64();
 }
 
 int smem_budget_bytes() {
@@ -278,6 +350,10 @@ int smem_budget_bytes() {
 
 int pick_bn(const styler_conv1d_args& a, int m_tiles) {
   if (a.ln_gamma != nullptr || a.dot_w != nullptr) return (a.N <= 256 && a.N % 16 == 0) ? a.N : 0;
+  static int forced = -1;   // tuning override: STYLER_TC_BN
+  if (forced < 0) { const char* e = getenv("STYLER_TC_BN"); forced = e != nullptr ? atoi(e) : 0; }
+  if (forced > 0 && forced % 16 == 0 && forced <= 256 && a.N % forced == 0 && (a.vt == nullptr || a.vt_col0 % forced == 0))
+    return forced;
   // largest tile that still gives >= 2 waves of CTAs; otherwise the smallest tile >= 64 (more CTAs);
   // otherwise the largest tile available.
   int largest = 0, smallest64 = 0;
@@ -307,7 +383,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   if (stages > 8) stages = 8;
   if (stages > num_kb) stages = num_kb;
   if (stages < 2) stages = num_kb >= 2 ? 2 : 1;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/;
   SB_REQUIRE(smem <= 227 * 1024, "conv1d_tc: smem %zu too large", smem);
 
   CUtensorMap tmA, tmB;
@@ -327,6 +403,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
     if (rc != 0) return rc;
   }
   EpiParams ep;
+  ep.dbg = (g_phase_buf != nullptr && m_tiles * n_tiles <= g_phase_cap) ? g_phase_buf : nullptr;
   ep.bias = a.bias; ep.act = a.act; ep.act2 = a.act2;
   ep.residual = a.residual; ep.r_bstride = a.r_bstride; ep.r_ld = a.r_ld; ep.res_f32 = a.residual_is_f32;
   ep.ln_gamma = a.ln_gamma; ep.ln_beta = a.ln_beta; ep.ln_eps = a.ln_eps;
@@ -372,6 +449,8 @@ bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why) {
   if (a.T < 1 || a.B < 1) return fail("empty problem");
   return true;
 }
+
+void set_phase_buffer(long long* buf, int cap) { g_phase_buf = buf; g_phase_cap = cap; }
 
 int conv1d_tc(const styler_conv1d_args& a, cudaStream_t s) {
   const char* why = nullptr;
