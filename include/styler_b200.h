@@ -68,8 +68,10 @@ int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream);
 
 /* ---- Scaled-dot-product multi-head self-attention (transformer/Modules.py:14-25, SubLayers.py:44-56) ----
  * qk: [B][T][2*H*64] (Q columns then K columns, head h at h*64; 1/temperature already folded into Q),
- * vt: [B][H*64][vt_ld] (V transposed), ctx: [B][T][H*64].  Keys >= lens[b] are masked (-inf); padded query
- * rows are computed like the reference.  The attention matrix is never written. */
+ * vt: [B][H*64][vt_ld] (V transposed) -- or NULL, in which case V is read row-major from qk's columns [2*H*64, 3*H*64)
+ * (qk is then the fused [B][T][3*H*64] QKV projection) and fed to the tensor core as an MN-major operand;
+ * ctx: [B][T][H*64].  Keys >= lens[b] are masked (-inf); padded query rows are computed like the reference.
+ * The attention matrix is never written. */
 int styler_attention_fwd(const void* qk, int64_t qk_bstride, int32_t qk_ld, const void* vt, int64_t vt_bstride,
                          int32_t vt_ld, const int64_t* lens, void* ctx, int64_t ctx_bstride, int32_t ctx_ld,
                          int32_t B, int32_t T, int32_t H, int32_t dtype, int32_t impl, void* stream);

@@ -57,9 +57,14 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const T* qk, long l
   __syncwarp();
   T* orow = ctx + b * ctx_bs + static_cast<long long>(tq) * ctx_ld + h * 64;
   for (int d = lane; d < 64; d += 32) {
-    const T* vrow = vt + b * vt_bs + static_cast<long long>(h * 64 + d) * vt_ld;
     float acc = 0.f;
-    for (int k = 0; k < len; ++k) acc = fmaf(p[k], DT<T>::ld(vrow + k), acc);
+    if (vt != nullptr) {
+      const T* vrow = vt + b * vt_bs + static_cast<long long>(h * 64 + d) * vt_ld;
+      for (int k = 0; k < len; ++k) acc = fmaf(p[k], DT<T>::ld(vrow + k), acc);
+    } else {   // V stored row-major next to Q and K: qk[b][k][2*D + h*64 + d]
+      const T* vcol = qk + b * qk_bs + 2 * D + h * 64 + d;
+      for (int k = 0; k < len; ++k) acc = fmaf(p[k], DT<T>::ld(vcol + static_cast<long long>(k) * qk_ld), acc);
+    }
     DT<T>::st(orow + d, len > 0 ? acc / sum : 0.f);
   }
 }
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const T* qk, long l
 // ----------------------------------------------------------------------------------------------- tcgen05
 constexpr int kQ = 128;    // queries per CTA
 constexpr int kKV = 128;   // keys per step
-constexpr int kThreadsTc = 192;
+constexpr int kThreadsTc = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two per TMEM lane quarter)
 
 __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2, flush-to-zero; inputs are <= 0 here
   float y;
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
                                                                   const __grid_constant__ CUtensorMap tmVT,
                                                                   const int64_t* __restrict__ lens, T* __restrict__ ctx,
                                                                   long long ctx_bs, int ctx_ld, int Tlen, int H,
-                                                                  int q_tiles) {
+                                                                  int q_tiles, int v_mn) {
   using C = AttnCfg<T>;
   constexpr bool kTf32 = C::es == 4;
   extern __shared__ uint8_t smem_raw[];
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 256);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -156,15 +161,20 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
         uint8_t* sV = sK + C::k_bytes;
         for (int sl = 0; sl < C::qk_slices; ++sl)
           tma_load_3d(sK + sl * kKV * 128, &tmQK, &kv_full[s], D + h * 64 + sl * C::bke, j * kKV, b);
-        for (int sl = 0; sl < C::pv_slices; ++sl)
-          tma_load_3d(sV + sl * 64 * 128, &tmVT, &kv_full[s], j * kKV + sl * C::bke, h * 64, b);
+        if (v_mn) {   // V row-major in the qkv tensor: [128 keys x 128-byte span of d] boxes, consumed as an MN-major B operand
+          for (int sl = 0; sl < C::qk_slices; ++sl)
+            tma_load_3d(sV + sl * kKV * 128, &tmQK, &kv_full[s], 2 * D + h * 64 + sl * C::bke, j * kKV, b);
+        } else {
+          for (int sl = 0; sl < C::pv_slices; ++sl)
+            tma_load_3d(sV + sl * 64 * 128, &tmVT, &kv_full[s], j * kKV + sl * C::bke, h * 64, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && nkt > 0) {
       const uint32_t fmt = kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16;
       const uint32_t idesc_s = umma_idesc(fmt, kQ, kKV);
-      const uint32_t idesc_o = umma_idesc(fmt, kQ, 64);
+      const uint32_t idesc_o = umma_idesc(fmt, kQ, 64, v_mn ? 1u : 0u);
       mbar_wait(q_full, 0);
       for (int j = 0; j < nkt; ++j) {
         const int s = j % C::kv_stages;
@@ -186,8 +196,9 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
 #pragma unroll
         for (int kk = 0; kk < kKV / C::umma_k; ++kk) {
           const int sl = (kk * 32) / 128, off = (kk * 32) % 128;
-          umma_ss<kTf32>(tmem_O, umma_desc_k_sw128(p_addr + sl * kQ * 128 + off),
-                         umma_desc_k_sw128(v_addr + sl * 64 * 128 + off), idesc_o, kk != 0 ? 1u : 0u);
+          const uint64_t bdesc = v_mn ? umma_desc_mn_sw128(v_addr + kk * C::umma_k * 128, kKV * 128, 1024)
+                                      : umma_desc_k_sw128(v_addr + sl * 64 * 128 + off);
+          umma_ss<kTf32>(tmem_O, umma_desc_k_sw128(p_addr + sl * kQ * 128 + off), bdesc, idesc_o, kk != 0 ? 1u : 0u);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[s]);
@@ -195,15 +206,19 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
     }
     __syncwarp();
   } else {
+    // 8 softmax warps: warp w may only touch TMEM lanes 32*(w%4)..+31, so each row (lane) is served by two threads:
+    // both scan all 128 score columns for the row max (cheap, keeps the running max identical in both), then each
+    // exponentiates / packs its own 64 key columns and accumulates its own 32 of the 64 output columns.
     const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;                    // column half handled by this thread
     const int r = q * 32 + lane;
     const int t = t0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     constexpr float kLog2e = 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     uint8_t* p_row = sP + r * 128;
     const int sw = r & 7;
     for (int j = 0; j < nkt; ++j) {
@@ -212,25 +227,29 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
       const int kbase = j * kKV;
       const bool full_tile = kbase + kKV <= len;           // only the last key tile needs the padding mask
       float mx = m_run;
-      for (int c = 0; c < kKV; c += 16) {
-        uint32_t raw[16];
-        tmem_ld16(tmem_S + lane_off + c, raw);
+      for (int c = 0; c < kKV; c += 32) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16(tmem_S + lane_off + c, ra);
+        tmem_ld16(tmem_S + lane_off + c + 16, rb);
         tmem_ld_wait();
         if (full_tile) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (kbase + c + i < len) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 16; ++i) {
+            if (kbase + c + i < len) mx = fmaxf(mx, __uint_as_float(ra[i]));
+            if (kbase + c + 16 + i < len) mx = fmaxf(mx, __uint_as_float(rb[i]));
+          }
         }
       }
       const float alpha = m_run == -INFINITY ? 0.f : fast_exp2((m_run - mx) * kLog2e);
       l_run *= alpha;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] *= alpha;
+      for (int i = 0; i < 32; ++i) o[i] *= alpha;
       const float mxl = mx * kLog2e;
-      for (int c = 0; c < kKV; c += 16) {
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c = hf * 64 + cc;
         uint32_t raw[16];
         tmem_ld16(tmem_S + lane_off + c, raw);
         tmem_ld_wait();
@@ -272,20 +291,25 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
       mbar_arrive(p_ready);
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 64; c += 16) {
-        uint32_t raw[16];
-        tmem_ld16(tmem_O + lane_off + c, raw);
+      {
+        uint32_t ra[16], rb[16];
+        tmem_ld16(tmem_O + lane_off + hf * 32, ra);
+        tmem_ld16(tmem_O + lane_off + hf * 32 + 16, rb);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[c + i] += __uint_as_float(raw[i]);
+        for (int i = 0; i < 16; ++i) { o[i] += __uint_as_float(ra[i]); o[16 + i] += __uint_as_float(rb[i]); }
       }
     }
+    // combine the two partial row sums through smem (the Q tile is dead once the last S MMA has completed)
+    float* s_l = reinterpret_cast<float*>(sQ);
+    s_l[hf * kQ + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = s_l[r] + s_l[kQ + r];
     if (t < Tlen) {
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      T* orow = ctx + b * ctx_bs + static_cast<long long>(t) * ctx_ld + h * 64;
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      T* orow = ctx + b * ctx_bs + static_cast<long long>(t) * ctx_ld + h * 64 + hf * 32;
 #pragma unroll
-      for (int c = 0; c < 64; c += 8) {
+      for (int c = 0; c < 32; c += 8) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = o[c + i] * inv;
@@ -303,15 +327,18 @@ int launch_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t 
               const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int Tlen, int H, cudaStream_t s) {
   using C = AttnCfg<T>;
   const int D = H * 64;
+  const int v_mn = vt == nullptr ? 1 : 0;
   CUtensorMap tmQK, tmVT;
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(2 * D), static_cast<uint64_t>(Tlen), static_cast<uint64_t>(B)};
+    const uint64_t dims[3] = {static_cast<uint64_t>((v_mn ? 3 : 2) * D), static_cast<uint64_t>(Tlen), static_cast<uint64_t>(B)};
     const uint64_t strides[2] = {static_cast<uint64_t>(qk_ld) * C::es, static_cast<uint64_t>(qk_bs) * C::es};
     const uint32_t box[3] = {static_cast<uint32_t>(C::bke), 128, 1};
     int rc = make_tmap(&tmQK, qk, C::es == 2 ? 1 : 0, 3, dims, strides, box);
     if (rc != 0) return rc;
   }
-  {
+  if (v_mn) {
+    tmVT = tmQK;
+  } else {
     const uint64_t dims[3] = {static_cast<uint64_t>(Tlen), static_cast<uint64_t>(D), static_cast<uint64_t>(B)};
     const uint64_t strides[2] = {static_cast<uint64_t>(vt_ld) * C::es, static_cast<uint64_t>(vt_bs) * C::es};
     const uint32_t box[3] = {static_cast<uint32_t>(C::bke), 64, 1};
@@ -326,7 +353,7 @@ int launch_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t 
   }
   const int q_tiles = ceil_div(Tlen, kQ);
   kern<<<B * H * q_tiles, kThreadsTc, C::smem, s>>>(tmQK, tmVT, lens, static_cast<T*>(ctx), ctx_bs, ctx_ld, Tlen, H,
-                                                    q_tiles);
+                                                    q_tiles, v_mn);
   SB_LAUNCH_OK();
   return 0;
 }
@@ -354,6 +381,8 @@ int attention_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64
                  const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int T, int H, int dtype,
                  cudaStream_t s) {
   const int es = dtype == STYLER_BF16 ? 2 : 4;
+  SB_REQUIRE(vt != nullptr || dtype == STYLER_BF16,
+             "attention_tc: row-major V (vt == NULL) is only validated for bf16; pass V^T for fp32/tf32");
   SB_REQUIRE((static_cast<int64_t>(ctx_ld) * es) % 16 == 0 && (ctx_bs * es) % 16 == 0 &&
                  (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
              "attention_tc: ctx must be 16-byte aligned/strided");
@@ -369,7 +398,7 @@ extern "C" int styler_attention_fwd(const void* qk, int64_t qk_bstride, int32_t 
                                     int64_t ctx_bstride, int32_t ctx_ld, int32_t B, int32_t T, int32_t H,
                                     int32_t dtype, int32_t impl, void* stream) {
   using namespace sb;
-  SB_REQUIRE(qk != nullptr && vt != nullptr && ctx != nullptr, "attention: null pointer");
+  SB_REQUIRE(qk != nullptr && ctx != nullptr, "attention: null pointer");
   SB_REQUIRE(B > 0 && T > 0 && H > 0, "attention: bad shape B=%d T=%d H=%d", B, T, H);
   SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "attention: bad dtype %d", dtype);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kAStageBytes = kBM * 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter, half the columns each)
 
 // Optional per-CTA phase timestamps (tools/phase_timing.py): 8 x int64 per CTA written with clock64():
 // [0] kernel entry  [1] after TMEM alloc + setup sync  [2] MMA thread: first stage full  [3] MMA thread: all issued
@@ -40,6 +40,7 @@ int g_phase_cap = 0;
 
 struct EpiParams {
   long long* dbg;
+  int stage_out, stage_res;   // 1: output rows / residual rows go through the freed pipeline smem with TMA (coalesced)
   const float* bias;
   int act, act2;
   const void* residual; long long r_bstride; int r_ld; int res_f32;
@@ -68,9 +69,15 @@ __device__ __forceinline__ void store16(T* p, const float (&v)[16]) {
   store8(p + 8, b);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+// ACT (activation before residual/LN) and LN are compile-time so each instance carries one tight epilogue loop: the
+// generic runtime-switched body was ~1850 SASS instructions per 32 columns (tanhf inlined 64x) and ran at ~7 clk/instr.
+// FAST: output staged through smem + TMA store, residual (if any) staged through smem, no V^T / fp32 copy / row dot:
+// the common case, compiled without the alternative paths (instruction issue, not memory, bounds this epilogue).
+template <typename T, int ACT, bool LN, bool FAST>
+__global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ CUtensorMap tmOut,
+                                                             const __grid_constant__ CUtensorMap tmRes,
                                                              const EpiParams ep, int Tlen, int n_tiles,
                                                              int tiles_per_utt, int KS, int pad, int kb_per_tap,
                                                              int BN, int stages) {
@@ -84,8 +91,10 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* res_full = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
   float* s_par = reinterpret_cast<float*>(smem + stages * stage_bytes + 256);   // [4][256]: bias, gamma, beta, dot_w
+  float* s_x = s_par + 1024;                                                    // [256 threads][4]: LN / dot exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = ep.dbg != nullptr ? ep.dbg + static_cast<long long>(blockIdx.x) * 8 : nullptr;
@@ -95,12 +104,17 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
   const int n0 = nt * BN;
   const int num_kb = KS * kb_per_tap;
   const uint32_t tmem_cols = tmem_cols_pow2(BN);
+  const bool tile_to_vt = !FAST && ep.vt != nullptr && n0 >= ep.vt_col0;
+  const bool st_out = FAST || (ep.stage_out != 0 && !tile_to_vt);            // TMA-store this tile's output from smem
+  const bool st_res = FAST ? ep.residual != nullptr : ep.stage_res != 0;      // TMA-load this tile's residual into smem
+  const int n_box = (BN * static_cast<int>(sizeof(T))) / 128;     // 16 KB [128 rows x 128 B] boxes per tile
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tmem_full, 1);
+    mbar_init(res_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -122,6 +136,12 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
         uint8_t* sa = smem + s * stage_bytes;
         tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap - pad, b);
         tma_load_3d(sa + kAStageBytes, &tmB, &full[s], kc, n0, tap);
+      }
+      if (st_res) {   // all MMAs done -> the pipeline stages are free: stage the residual tile there
+        mbar_wait(tmem_full, 0);
+        mbar_arrive_expect_tx(res_full, n_box * kAStageBytes);
+        for (int bx = 0; bx < n_box; ++bx)
+          tma_load_3d(smem + bx * kAStageBytes, &tmRes, res_full, n0 + bx * kBKE, t0, b);
       }
     }
   } else if (warp == 1) {
@@ -148,27 +168,33 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------------ epilogue (8 warps; 128 TMEM lanes x 2 column halves)
+    // A warp may only read TMEM lanes 32*(warp%4)..+31, so every output row is served by two threads, each owning
+    // half of the tile's columns: one warp per scheduler was latency-bound (~7 clk/instr), two halve the critical path.
     const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int r = q * 32 + lane;
+    const bool split = (BN % 32) == 0;
+    const int c_begin = split ? hf * (BN / 2) : (hf == 0 ? 0 : BN);
+    const int c_end = split ? c_begin + BN / 2 : BN;
     const int t = t0 + r;
     const bool row_ok = t < Tlen;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool masked = ep.lens != nullptr && row_ok && t >= static_cast<int>(ep.lens[b]);
-    const bool has_ln = ep.ln_gamma != nullptr;
+    constexpr bool has_ln = LN;
     const bool has_res = ep.residual != nullptr;
-    const bool to_vt = ep.vt != nullptr && n0 >= ep.vt_col0;
+    const bool to_vt = tile_to_vt;
     const T* res_row = nullptr;
     const float* res_row_f = nullptr;
-    if (has_res) {
+    if (has_res && !FAST) {
       const long long off = b * ep.r_bstride + static_cast<long long>(t) * ep.r_ld + n0;
       if (ep.res_f32) res_row_f = static_cast<const float*>(ep.residual) + off;
       else res_row = static_cast<const T*>(ep.residual) + off;
     }
-    T* out_row = ep.out != nullptr
+    T* out_row = !FAST && ep.out != nullptr
                      ? static_cast<T*>(ep.out) + b * ep.o_bstride + static_cast<long long>(t) * ep.o_ld + n0
                      : nullptr;
-    float* of_row = ep.out_f32 != nullptr
+    float* of_row = !FAST && ep.out_f32 != nullptr
                         ? ep.out_f32 + b * ep.of_bstride + static_cast<long long>(t) * ep.of_ld + n0
                         : nullptr;
     T* vt_base = to_vt ? static_cast<T*>(ep.vt) + b * ep.vt_bstride +
@@ -179,34 +205,99 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
     // 16 dependent global loads per chunk was the dominant epilogue cost.
     {
       const int te = threadIdx.x - 64;
-      for (int i = te; i < BN; i += 128) {
+      for (int i = te; i < BN; i += 256) {
         s_par[i] = ep.bias != nullptr ? ep.bias[n0 + i] : 0.f;
         s_par[256 + i] = has_ln ? ep.ln_gamma[n0 + i] : 1.f;
         s_par[512 + i] = has_ln ? ep.ln_beta[n0 + i] : 0.f;
         s_par[768 + i] = ep.dot_w != nullptr ? ep.dot_w[n0 + i] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const float* s_bias = s_par;
     const float* s_gamma = s_par + 256;
     const float* s_beta = s_par + 512;
     const float* s_dot = s_par + 768;
-
-    auto load_res = [&](int c, float (&rr)[16]) {       // residual columns c..c+15 of this thread's row
-      if (res_row_f != nullptr) load16(res_row_f + c, rr); else load16(res_row + c, rr);
+    auto ld16s = [](const float* p, float (&o)[16]) {   // 16 consecutive smem floats as 4 x LDS.128 (p is 64-byte aligned)
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        const float4 f = reinterpret_cast<const float4*>(p)[g4];
+        o[4 * g4] = f.x; o[4 * g4 + 1] = f.y; o[4 * g4 + 2] = f.z; o[4 * g4 + 3] = f.w;
+      }
     };
-    auto act_inplace = [&](float (&v)[16], int act) {
-      if (act == STYLER_ACT_RELU) {
+
+    // smem staging address of columns c..c+15 of this thread's row: box (c*es/128), 128-byte row r, 16-byte chunks XOR (r&7)
+    uint8_t* stage_row = smem + r * 128;
+    const int sw = r & 7;
+    auto stage_ptr = [&](int c, int chunk) -> uint8_t* {
+      const int byte0 = c * static_cast<int>(sizeof(T));
+      return stage_row + (byte0 / 128) * kAStageBytes + ((((byte0 % 128) / 16 + chunk) ^ sw) * 16);
+    };
+    auto load_res = [&](int c, float (&rr)[16]) {       // residual columns c..c+15 of this thread's row
+      if (FAST || st_res) {
+        if constexpr (sizeof(T) == 2) {
+          float a[8], bq[8];
+          load8(reinterpret_cast<const T*>(stage_ptr(c, 0)), a);
+          load8(reinterpret_cast<const T*>(stage_ptr(c, 1)), bq);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { rr[i] = a[i]; rr[8 + i] = bq[i]; }
+        } else {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 f = *reinterpret_cast<const float4*>(stage_ptr(c, g4));
+            rr[4 * g4] = f.x; rr[4 * g4 + 1] = f.y; rr[4 * g4 + 2] = f.z; rr[4 * g4 + 3] = f.w;
+          }
+        }
+      } else if (res_row_f != nullptr) {
+        load16(res_row_f + c, rr);
+      } else {
+        load16(res_row + c, rr);
+      }
+    };
+    auto store_out = [&](int c, const float (&v)[16]) {   // output columns c..c+15 (dtype T)
+      if (FAST || st_out) {
+        if constexpr (sizeof(T) == 2) {
+          float a[8], bq[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a[i] = v[i]; bq[i] = v[8 + i]; }
+          store8(reinterpret_cast<T*>(stage_ptr(c, 0)), a);
+          store8(reinterpret_cast<T*>(stage_ptr(c, 1)), bq);
+        } else {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4)
+            *reinterpret_cast<float4*>(stage_ptr(c, g4)) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+        }
+      } else if (out_row != nullptr && row_ok) {
+        store16(out_row + c, v);
+      }
+    };
+    auto act1 = [&](float (&v)[16]) {                  // compile-time activation (before residual / LayerNorm)
+      if constexpr (ACT == STYLER_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      } else if (act == STYLER_ACT_TANH) {
+      } else if constexpr (ACT == STYLER_ACT_TANH) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+        for (int i = 0; i < 16; ++i) {
+          if constexpr (sizeof(T) == 2) {              // bf16 storage: MUFU.TANH (rel. error 2^-11 < bf16 rounding)
+            float y;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(v[i]));
+            v[i] = y;
+          } else {
+            v[i] = tanhf(v[i]);
+          }
+        }
+      }
+    };
+    const bool relu2 = ep.act2 == STYLER_ACT_RELU;     // post-LN activation: only none|relu on this path
+    auto act2f = [&](float (&v)[16]) {
+      if (relu2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
       }
     };
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (st_res) mbar_wait(res_full, 0);
     if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
 
     float mean = 0.f, rstd = 1.f;
@@ -214,34 +305,37 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
       // pass 1: v = act(acc + bias) + residual, parked back in TMEM; shifted sums for mean/variance.
       // Two 16-column chunks per iteration so TMEM and residual loads of both are in flight together.
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
-      for (int c = 0; c < BN; c += 32) {
-        const bool two = c + 16 < BN;
+      for (int c = c_begin; c < c_end; c += 32) {
+        const bool two = c + 16 < c_end;
         uint32_t ra[16], rb[16];
         float xa[16], xb[16];
         tmem_ld16(taddr + c, ra);
         if (two) tmem_ld16(taddr + c + 16, rb);
-        if (has_res && row_ok) { load_res(c, xa); if (two) load_res(c + 16, xb); }
+        const bool do_res = has_res && (row_ok || st_res);
+        if (do_res) { load_res(c, xa); if (two) load_res(c + 16, xb); }
         tmem_ld_wait();
         {
-          float v[16];
+          float v[16], pb[16];
+          ld16s(s_bias + c, pb);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + s_bias[c + i];
-          act_inplace(v, ep.act);
-          if (has_res && row_ok) {
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + pb[i];
+          act1(v);
+          if (do_res) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += xa[i];
           }
-          if (c == 0) shift = v[0];
+          if (c == c_begin) shift = v[0];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1 += d; s2 += d * d; ra[i] = __float_as_uint(v[i]); }
           tmem_st16(taddr + c, ra);
         }
         if (two) {
-          float v[16];
+          float v[16], pb[16];
+          ld16s(s_bias + c + 16, pb);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + s_bias[c + 16 + i];
-          act_inplace(v, ep.act);
-          if (has_res && row_ok) {
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + pb[i];
+          act1(v);
+          if (do_res) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += xb[i];
           }
@@ -251,31 +345,42 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
         }
       }
       tmem_st_wait();
+      // combine the two half-row statistics (shifted sums are merged exactly; n_h = columns owned by half h)
+      float* mine = s_x + (hf * 128 + r) * 4;
+      mine[0] = shift; mine[1] = s1; mine[2] = s2;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* h0 = s_x + r * 4;
+      const float* h1 = s_x + (128 + r) * 4;
+      const float n0f = static_cast<float>(split ? BN / 2 : BN), n1f = static_cast<float>(split ? BN / 2 : 0);
       const float inv_n = 1.0f / static_cast<float>(BN);
-      const float dm = s1 * inv_n;
-      mean = shift + dm;
-      const float var = fmaxf(s2 * inv_n - dm * dm, 0.f);
+      mean = (n0f * h0[0] + h0[1] + n1f * h1[0] + h1[1]) * inv_n;
+      const float d0 = mean - h0[0], d1 = mean - h1[0];
+      const float var = fmaxf((h0[2] - 2.f * d0 * h0[1] + n0f * d0 * d0 + h1[2] - 2.f * d1 * h1[1] + n1f * d1 * d1) * inv_n, 0.f);
       rstd = rsqrtf(var + ep.ln_eps);
     }
-    if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
+    if (dbg != nullptr && threadIdx.x == 64 && has_ln) dbg[5] = clock64();
 
     float dot = 0.f;
-    const bool has_dot = ep.dot_w != nullptr;
+    const bool has_dot = !FAST && ep.dot_w != nullptr;
     auto finish_chunk = [&](int c, float (&v)[16]) {   // v = final values of columns c..c+15
       if (has_dot) {
+        float pd[16];
+        ld16s(s_dot + c, pd);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dot = fmaf(v[i], s_dot[c + i], dot);
+        for (int i = 0; i < 16; ++i) dot = fmaf(v[i], pd[i], dot);
       }
       if (masked) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
-      if (row_ok) {
-        if (to_vt) {
+      if (to_vt) {
+        if (row_ok) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) DT<T>::st(vt_base + static_cast<long long>(c + i) * ep.vt_ld, v[i]);
-        } else {
-          if (out_row != nullptr) store16(out_row + c, v);
+        }
+      } else {
+        store_out(c, v);
+        if (row_ok) {
           if (of_row != nullptr) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
@@ -284,51 +389,77 @@ __global__ void __launch_bounds__(kThreads) conv1d_tc_kernel(const __grid_consta
         }
       }
     };
-    for (int c = 0; c < BN; c += 32) {
-      const bool two = c + 16 < BN;
+    long long t_wait = 0;
+    for (int c = c_begin; c < c_end; c += 32) {
+      const bool two = c + 16 < c_end;
       uint32_t ra[16], rb[16];
       float xa[16], xb[16];
+      long long tq0 = 0;
+      if (dbg != nullptr) tq0 = clock64();
       tmem_ld16(taddr + c, ra);
       if (two) tmem_ld16(taddr + c + 16, rb);
-      const bool need_res = has_res && !has_ln && row_ok;
+      const bool need_res = has_res && !has_ln && (row_ok || st_res);
       if (need_res) { load_res(c, xa); if (two) load_res(c + 16, xb); }
       tmem_ld_wait();
-      float v[16];
+      if (dbg != nullptr) t_wait += clock64() - tq0;
+      float v[16], pa[16], pb[16];
       if (has_ln) {
+        ld16s(s_gamma + c, pa);
+        ld16s(s_beta + c, pb);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(ra[i]) - mean) * rstd * s_gamma[c + i] + s_beta[c + i];
+        for (int i = 0; i < 16; ++i) v[i] = fmaf((__uint_as_float(ra[i]) - mean) * rstd, pa[i], pb[i]);
       } else {
+        ld16s(s_bias + c, pb);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + s_bias[c + i];
-        act_inplace(v, ep.act);
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + pb[i];
+        act1(v);
         if (need_res) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += xa[i];
         }
       }
-      act_inplace(v, ep.act2);
+      act2f(v);
       finish_chunk(c, v);
       if (two) {
         if (has_ln) {
+          ld16s(s_gamma + c + 16, pa);
+          ld16s(s_beta + c + 16, pb);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = (__uint_as_float(rb[i]) - mean) * rstd * s_gamma[c + 16 + i] + s_beta[c + 16 + i];
+          for (int i = 0; i < 16; ++i) v[i] = fmaf((__uint_as_float(rb[i]) - mean) * rstd, pa[i], pb[i]);
         } else {
+          ld16s(s_bias + c + 16, pb);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + s_bias[c + 16 + i];
-          act_inplace(v, ep.act);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + pb[i];
+          act1(v);
           if (need_res) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += xb[i];
           }
         }
-        act_inplace(v, ep.act2);
+        act2f(v);
         finish_chunk(c + 16, v);
       }
     }
-    if (ep.dot_out != nullptr && row_ok)
-      ep.dot_out[static_cast<long long>(b) * Tlen + t] = masked ? 0.f : dot + ep.dot_b;
-    if (dbg != nullptr && threadIdx.x == 64) dbg[6] = clock64();
+    if (!FAST && ep.dot_out != nullptr) {               // row dot: sum the two column halves
+      if (has_ln) asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone has consumed the LN exchange slots
+      s_x[(hf * 128 + r) * 4 + 3] = dot;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (hf == 0 && row_ok)
+        ep.dot_out[static_cast<long long>(b) * Tlen + t] = masked ? 0.f : s_x[r * 4 + 3] + s_x[(128 + r) * 4 + 3] + ep.dot_b;
+    }
+    if (dbg != nullptr && threadIdx.x == 64 && !has_ln) dbg[5] = dbg[4] + t_wait;   // non-LN tiles: slot 5 = TMEM ld+wait time
+    long long t_pre_store = 0;
+    if (dbg != nullptr) t_pre_store = clock64();
+    if (st_out) {   // smem tile -> global with TMA (rows >= T are clipped by the tensor map)
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+        for (int bx = 0; bx < n_box; ++bx) tma_store_3d(&tmOut, smem + bx * kAStageBytes, n0 + bx * kBKE, t0, b);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+    }
+    if (dbg != nullptr && threadIdx.x == 64) { dbg[6] = clock64(); if (!has_ln) dbg[3] = t_pre_store; }
   }
 
   tc_fence_before();
@@ -383,7 +514,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   if (stages > 8) stages = 8;
   if (stages > num_kb) stages = num_kb;
   if (stages < 2) stages = num_kb >= 2 ? 2 : 1;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/ + 4096 /*exchange*/;
   SB_REQUIRE(smem <= 227 * 1024, "conv1d_tc: smem %zu too large", smem);
 
   CUtensorMap tmA, tmB;
@@ -402,7 +533,31 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
     int rc = make_tmap(&tmB, a.w, es == 2 ? 1 : 0, 3, dims, strides, box);
     if (rc != 0) return rc;
   }
+  // Coalesced epilogue I/O through the (by then idle) pipeline smem: needs whole 128-byte boxes and room for the tile.
+  const bool boxes_ok = (BN * es) % 128 == 0 && static_cast<size_t>(BN) * es * 128 <= static_cast<size_t>(stages) * stage_bytes;
+  const bool stage_out = a.out != nullptr && boxes_ok;
+  const bool stage_res = a.residual != nullptr && !a.residual_is_f32 && a.r_ld != 0 && boxes_ok;
+  CUtensorMap tmOut = tmA, tmRes = tmA;
+  if (stage_out) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(a.vt != nullptr ? a.vt_col0 : a.N), static_cast<uint64_t>(a.T),
+                              static_cast<uint64_t>(a.B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(a.o_ld) * es,
+                                 static_cast<uint64_t>(a.B > 1 ? a.o_bstride : static_cast<int64_t>(a.o_ld) * a.T) * es};
+    const uint32_t box[3] = {static_cast<uint32_t>(bke), static_cast<uint32_t>(kBM), 1};
+    int rc = make_tmap(&tmOut, a.out, es == 2 ? 1 : 2, 3, dims, strides, box);
+    if (rc != 0) return rc;
+  }
+  if (stage_res) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.T), static_cast<uint64_t>(a.B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(a.r_ld) * es,
+                                 static_cast<uint64_t>(a.B > 1 ? a.r_bstride : static_cast<int64_t>(a.r_ld) * a.T) * es};
+    const uint32_t box[3] = {static_cast<uint32_t>(bke), static_cast<uint32_t>(kBM), 1};
+    int rc = make_tmap(&tmRes, a.residual, es == 2 ? 1 : 2, 3, dims, strides, box);
+    if (rc != 0) return rc;
+  }
   EpiParams ep;
+  ep.stage_out = stage_out ? 1 : 0;
+  ep.stage_res = stage_res ? 1 : 0;
   ep.dbg = (g_phase_buf != nullptr && m_tiles * n_tiles <= g_phase_cap) ? g_phase_buf : nullptr;
   ep.bias = a.bias; ep.act = a.act; ep.act2 = a.act2;
   ep.residual = a.residual; ep.r_bstride = a.r_bstride; ep.r_ld = a.r_ld; ep.res_f32 = a.residual_is_f32;
@@ -413,13 +568,26 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   ep.out_f32 = a.out_f32; ep.of_bstride = a.of_bstride; ep.of_ld = a.of_ld;
   ep.vt = a.vt; ep.vt_col0 = a.vt_col0; ep.vt_bstride = a.vt_bstride; ep.vt_ld = a.vt_ld;
 
-  auto kern = conv1d_tc_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, EpiParams, int, int, int, int, int, int, int, int);
+#define SB_K(A, L, F) conv1d_tc_kernel<T, A, L, F>
+  static const KernFn table[3][2][2] = {
+      {{SB_K(STYLER_ACT_NONE, false, false), SB_K(STYLER_ACT_NONE, false, true)},
+       {SB_K(STYLER_ACT_NONE, true, false), SB_K(STYLER_ACT_NONE, true, true)}},
+      {{SB_K(STYLER_ACT_RELU, false, false), SB_K(STYLER_ACT_RELU, false, true)},
+       {SB_K(STYLER_ACT_RELU, true, false), SB_K(STYLER_ACT_RELU, true, true)}},
+      {{SB_K(STYLER_ACT_TANH, false, false), SB_K(STYLER_ACT_TANH, false, true)},
+       {SB_K(STYLER_ACT_TANH, true, false), SB_K(STYLER_ACT_TANH, true, true)}}};
+#undef SB_K
+  static bool attr_set[3][2][2] = {};
+  const int ia = a.act, il = a.ln_gamma != nullptr ? 1 : 0;
+  const int ifast = (stage_out && a.vt == nullptr && a.out_f32 == nullptr && a.dot_w == nullptr &&
+                     (a.residual == nullptr || stage_res)) ? 1 : 0;
+  KernFn kern = table[ia][il][ifast];
+  if (!attr_set[ia][il][ifast]) {
     SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set[ia][il][ifast] = true;
   }
-  kern<<<m_tiles * n_tiles, kThreads, smem, stream>>>(tmA, tmB, ep, a.T, n_tiles, tiles_per_utt, a.KS, a.pad,
+  kern<<<m_tiles * n_tiles, kThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles, tiles_per_utt, a.KS, a.pad,
                                                       kb_per_tap, BN, stages);
   SB_LAUNCH_OK();
   return 0;
@@ -447,6 +615,8 @@ bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why) {
     return fail("residual not 16-byte aligned/strided");
   if (a.vt != nullptr && a.vt_col0 % 16 != 0) return fail("vt_col0 not a multiple of 16");
   if (a.T < 1 || a.B < 1) return fail("empty problem");
+  if (a.act < 0 || a.act > 2) return fail("bad act");
+  if (a.act2 != STYLER_ACT_NONE && a.act2 != STYLER_ACT_RELU) return fail("act2 must be none|relu on the tensor-core path");
   return true;
 }
 

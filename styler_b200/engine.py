@@ -48,6 +48,10 @@ class Engine:
         self.attn_impl = IMPL_SIMT if precision == "fp32" else IMPL_TC
         self._pos_cache = {}
         self.inter = {}
+        self.v_rowmajor = precision == "bf16"   # attention reads V row-major from the fused QKV buffer (MN-major B operand;
+                                               # validated for kind::f16 only -- the fp32 modes keep the transposed-V layout)
+        self.use_streams = True   # run the four audio-encoder branches on side streams
+        self._streams = None
         self.prof = None   # bench.py: list collecting (start_event, end_event, B, T) around the dominant kernel (FFN conv k9)
         self._pack({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
 
@@ -164,11 +168,15 @@ class Engine:
     def fft_block(self, x, lens, W, out=None):
         """transformer/Layers.py:26-34: MHA -> zero padded rows -> Conv1d FFN -> zero padded rows."""
         B, T, _ = x.shape
-        Tp = (T + 7) // 8 * 8
-        qk = torch.empty(B, T, 512, device=x.device, dtype=self.dt)
-        vt = torch.empty(B, 256, Tp, device=x.device, dtype=self.dt)
-        ops.conv1d(x, W.wqkv, W.bqkv, out=qk, vt=vt, vt_col0=512, impl=self.impl)
-        ctx = ops.attention(qk, vt, lens, 4, impl=self.attn_impl)
+        if self.v_rowmajor:   # fused QKV rows; V consumed as an MN-major tensor-core operand (no transposed store)
+            qkv = ops.conv1d(x, W.wqkv, W.bqkv, impl=self.impl)
+            ctx = ops.attention(qkv, None, lens, 4, impl=self.attn_impl)
+        else:
+            Tp = (T + 7) // 8 * 8
+            qk = torch.empty(B, T, 512, device=x.device, dtype=self.dt)
+            vt = torch.empty(B, 256, Tp, device=x.device, dtype=self.dt)
+            ops.conv1d(x, W.wqkv, W.bqkv, out=qk, vt=vt, vt_col0=512, impl=self.impl)
+            ctx = ops.attention(qk, vt, lens, 4, impl=self.attn_impl)
         y1 = ops.conv1d(ctx, W.wfc, W.bfc, residual=x, ln=W.ln1, lens=lens, impl=self.impl)
         if self.prof is not None:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -194,26 +202,50 @@ class Engine:
                           want_out=self.precision == "fp32", impl=self.impl)
         return d
 
-    def audio_encoder(self, mel_target, p_idx, e_idx, mel_aug, mel_len, src_len, L):
-        """modules.py:164-201 on the padded grid: conv stacks + GroupNorm + ReLU @Tr, Mel Calibrator, 2-layer BiLSTMs @L."""
-        outs = []
+    def _audio_branch(self, br, xin, mel_len, src_len, L):
+        x = None
+        for j, (cw, cb, g, be) in enumerate(br.convs):
+            if j == 0 and br.onehot:
+                x = ops.onehot_conv(xin, cw, cb, self.dt)
+            else:
+                x = ops.conv1d(xin if j == 0 else x, cw, cb, pad=2, impl=self.impl)
+            ops.groupnorm_relu_(x, g, be, 16, 1e-5)
+        c = ops.mel_calibrator(x, mel_len, src_len, L)
+        for (wih, bias, whh) in br.lstm:
+            B = c.shape[0]
+            gx = torch.empty(B, L, wih.shape[1], device=c.device, dtype=torch.float32)
+            ops.conv1d(c, wih, bias, out_f32=gx, want_out=False, impl=self.impl)
+            c = ops.bilstm_layer(gx, whh, self.dt)
+        return c
+
+    def audio_encoder(self, mel_target, p_idx, e_idx, mel_aug, mel_len, src_len, L, join=True):
+        """modules.py:164-201 on the padded grid: conv stacks + GroupNorm + ReLU @Tr, Mel Calibrator, 2-layer BiLSTMs @L.
+        The four style-factor branches are independent: each runs on its own CUDA stream so the latency-bound BiLSTM
+        recurrences (64 CTAs) overlap the other branches' convolutions instead of serialising."""
         ins = (mel_target, p_idx, e_idx, mel_aug)
-        for br, xin in zip(self.w.branches, ins):
-            x = None
-            for j, (cw, cb, g, be) in enumerate(br.convs):
-                if j == 0 and br.onehot:
-                    x = ops.onehot_conv(xin, cw, cb, self.dt)
-                else:
-                    x = ops.conv1d(xin if j == 0 else x, cw, cb, pad=2, impl=self.impl)
-                ops.groupnorm_relu_(x, g, be, 16, 1e-5)
-            c = ops.mel_calibrator(x, mel_len, src_len, L)
-            for (wih, bias, whh) in br.lstm:
-                B = c.shape[0]
-                gx = torch.empty(B, L, wih.shape[1], device=c.device, dtype=torch.float32)
-                ops.conv1d(c, wih, bias, out_f32=gx, want_out=False, impl=self.impl)
-                c = ops.bilstm_layer(gx, whh, self.dt)
+        if not self.use_streams:
+            return [self._audio_branch(br, xin, mel_len, src_len, L) for br, xin in zip(self.w.branches, ins)]
+        main = torch.cuda.current_stream(self.device)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
+        start = torch.cuda.Event()
+        start.record(main)
+        outs = []
+        for st, br, xin in zip(self._streams, self.w.branches, ins):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                c = self._audio_branch(br, xin, mel_len, src_len, L)
+            c.record_stream(main)
             outs.append(c)
+        if join:
+            self.join_audio_streams()
         return outs
+
+    def join_audio_streams(self):
+        if self.use_streams and self._streams is not None:
+            main = torch.cuda.current_stream(self.device)
+            for st in self._streams:
+                main.wait_stream(st)
 
     def _mlp2(self, x, W, out=None):
         h = ops.conv1d(x, W[0], W[1], act=ACT_RELU, impl=self.impl)
@@ -257,23 +289,25 @@ class Engine:
         B, L = src_seq.shape
         dev = self.device
         enc = torch.empty(B, L, 1280, device=dev, dtype=self.dt)
+        # the audio-encoder branches (side streams) overlap the text encoder and speaker projections (this stream)
+        p_idx, e_idx = ops.quantize_index(p_norm), ops.quantize_index(e_input)                          # utils.py:417-429
+        mel_t, mel_a = self._act(mel_target), self._act(mel_aug)
+        d_enc, p_enc, e_enc, n_enc = self.audio_encoder(mel_t, p_idx, e_idx, mel_a, mel_len, src_len, L, join=False)
         text = self.text_encoder(src_seq, src_len, out=enc[..., 0:256])
         neck = ops.conv1d(text, w.tld[0], w.tld[1], act=ACT_RELU, impl=self.impl)                      # [B,L,4]
         spk_in = self._act(speaker_embed).unsqueeze(0)                                                  # [1,B,512]
         spk_p = ops.conv1d(spk_in, w.slp[0], w.slp[1], act=ACT_RELU, impl=self.impl)[0]                 # [B,128]
         spk = ops.conv1d(spk_in, w.sl[0], w.sl[1], act=ACT_RELU, impl=self.impl)[0]                     # [B,256]
-        p_idx, e_idx = ops.quantize_index(p_norm), ops.quantize_index(e_input)                          # utils.py:417-429
-        d_enc, p_enc, e_enc, n_enc = self.audio_encoder(self._act(mel_target), p_idx, e_idx, self._act(mel_aug),
-                                                        mel_len, src_len, L)
+        neck_up = ops.conv1d(neck, w.tlu[0], w.tlu[1], act=ACT_RELU, impl=self.impl)                    # [B,L,256]
+        ops.add(None, rowvec=spk, out=enc[..., 512:768])
+        self.join_audio_streams()
         post = tuple(self._classifier(x, w.cls[n]) for x, n in ((d_enc, "d"), (p_enc, "p"), (e_enc, "e")))
         p_enc_sp = ops.add(p_enc, rowvec=spk_p)                                                         # modules.py:332
         d_up = self._mlp2(d_enc, w.mlp["duration"])
         p_up = self._mlp2(p_enc_sp, w.mlp["pitch"])
         e_up = self._mlp2(e_enc, w.mlp["energy"])
         n_up = self._mlp2(n_enc, w.mlp["residual"], out=enc[..., 1024:1280])
-        neck_up = ops.conv1d(neck, w.tlu[0], w.tlu[1], act=ACT_RELU, impl=self.impl)                    # [B,L,256]
         ops.add(neck_up, p_up, out=enc[..., 256:512])                                                   # modules.py:350
-        ops.add(None, rowvec=spk, out=enc[..., 512:768])
         ops.add(neck_up, e_up, out=enc[..., 768:1024])
         dur_in = ops.add(neck_up, d_up)
         log_d = self.predictor(dur_in, src_len, w.pred["duration"])                                     # modules.py:353

@@ -89,14 +89,16 @@ def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=
 
 
 def attention(qk, vt, lens, n_head=4, *, out=None, impl=IMPL_AUTO):
-    """ctx[B,T,H*64] = softmax(mask(Q K^T)) V ; qk [B,T,2*H*64] (Q pre-scaled), vt [B,H*64,Tpad]."""
+    """ctx[B,T,H*64] = softmax(mask(Q K^T)) V ; qk [B,T,2*H*64] (Q pre-scaled) + vt [B,H*64,Tpad], or the fused
+    qkv [B,T,3*H*64] with vt=None (V read row-major)."""
     qk, qk_bs, qk_ld = _v3(qk, "qk")
     B, T, _ = qk.shape
     D = n_head * 64
     if out is None:
         out = torch.empty(B, T, D, device=qk.device, dtype=qk.dtype)
     o, o_bs, o_ld = _v3(out, "ctx")
-    L.check(L.lib().styler_attention_fwd(L.ptr(qk), qk_bs, qk_ld, L.ptr(vt), int(vt.stride(0)), int(vt.stride(1)),
+    L.check(L.lib().styler_attention_fwd(L.ptr(qk), qk_bs, qk_ld, L.ptr(vt), int(vt.stride(0)) if vt is not None else 0,
+                                         int(vt.stride(1)) if vt is not None else 0,
                                          L.ptr(lens), L.ptr(o), o_bs, o_ld, B, T, n_head, L.dtype_code(qk.dtype), impl,
                                          L.stream_ptr()), "attention")
     return out

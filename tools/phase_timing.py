@@ -53,3 +53,7 @@ for name, fn in cases.items():
     life = (st[:, 7] - st[:, 0]).double()
     print("%-10s %7.1f us  ctas=%d  lifetime med %.0f clk | " % (name, e0.elapsed_time(e1) * 1e3, st.shape[0], life.median()) +
           "  ".join("%s %.0f" % (n, d[:, i].median()) for i, n in enumerate(names)), flush=True)
+    if "ln" not in name:   # non-LN tiles: slot5-slot4 = time in TMEM ld+wait, slot6-slot3 = TMA-store tail (slot3 reused)
+        print("           epilogue detail: tmem ld+wait %.0f clk, compute+smem store %.0f clk, tma store tail %.0f clk" % (
+            (st[:, 5] - st[:, 4]).double().median(), ((st[:, 3] - st[:, 4]) - (st[:, 5] - st[:, 4])).double().median(),
+            (st[:, 6] - st[:, 3]).double().median()), flush=True)
