@@ -485,17 +485,23 @@ int pick_bn(const styler_conv1d_args& a, int m_tiles) {
   if (forced < 0) { const char* e = getenv("STYLER_TC_BN"); forced = e != nullptr ? atoi(e) : 0; }
   if (forced > 0 && forced % 16 == 0 && forced <= 256 && a.N % forced == 0 && (a.vt == nullptr || a.vt_col0 % forced == 0))
     return forced;
-  // largest tile that still gives >= 2 waves of CTAs; otherwise the smallest tile >= 64 (more CTAs);
-  // otherwise the largest tile available.
-  int largest = 0, smallest64 = 0;
-  for (int bn = 256; bn >= 16; bn -= 16) {
-    if (a.N % bn != 0) continue;
-    if (a.vt != nullptr && a.vt_col0 % bn != 0) continue;
-    if (largest == 0) largest = bn;
-    if (static_cast<long long>(m_tiles) * (a.N / bn) >= 296) return bn;
-    if (bn >= 64) smallest64 = bn;
+  // Prefer tiles whose rows are whole 128-byte boxes (coalesced TMA epilogue); among those the largest tile that still
+  // gives >= 2 waves of CTAs, otherwise the smallest tile >= 64 (more CTAs), otherwise the largest tile available.
+  const int es = a.dtype == STYLER_BF16 ? 2 : 4;
+  for (int pass = 0; pass < 2; ++pass) {
+    int largest = 0, smallest64 = 0;
+    for (int bn = 256; bn >= 16; bn -= 16) {
+      if (a.N % bn != 0) continue;
+      if (a.vt != nullptr && a.vt_col0 % bn != 0) continue;
+      if (pass == 0 && ((bn * es) % 128 != 0 || a.out == nullptr)) continue;
+      if (largest == 0) largest = bn;
+      if (static_cast<long long>(m_tiles) * (a.N / bn) >= 296) return bn;
+      if (bn >= 64) smallest64 = bn;
+    }
+    if (smallest64 != 0) return smallest64;
+    if (largest != 0) return largest;
   }
-  return smallest64 != 0 ? smallest64 : largest;
+  return 0;
 }
 
 template <typename T>

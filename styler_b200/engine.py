@@ -329,9 +329,13 @@ class Engine:
         p_pred = self.predictor(p_in, lens, w.pred["pitch"])
         p_val, p_scale = (p_target.to(self.device, torch.float32).contiguous(), 1.0) if p_target is not None else (p_pred, float(p_control))
         e_val, e_scale = (e_target.to(self.device, torch.float32).contiguous(), 1.0) if e_target is not None else (e_pred, float(e_control))
+        # clean and noisy decoder inputs land in one [2B,T,256] buffer so both decodes run as a single batched pass
+        B = encT.shape[0]
+        xx = torch.empty(2 * B, T, 256, device=encT.device, dtype=self.dt)
         x, x_noisy, _, _ = ops.bucket_embed_sum(encT[..., 0:256], encT[..., 512:768], encT[..., 1024:1280], p_val, e_val,
                                                 p_scale, e_scale, w.pitch_bins, w.energy_bins, w.pitch_emb, w.energy_emb,
-                                                want_noisy=True)
+                                                want_noisy=True, out=xx[:B], out_noisy=xx[B:])
+        self._xx = xx
         return x, x_noisy, encT, p_pred, e_pred, mel_len
 
     def forward(self, src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target=None, p_target=None,
@@ -360,8 +364,10 @@ class Engine:
             T = int(max_mel_len) if max_mel_len else int(tot.max().item())     # the one host sync of the path
             x, x_noisy, _, p_pred, e_pred, out_len = self.variance_adapt(enc, log_d, T, None, None, p_target, e_target,
                                                                          d_control, p_control, e_control, duration=duration)
-        mel, post_mel = self.decode(x, out_len)
-        mel_n, post_mel_n = self.decode(x_noisy, out_len)
+        # styler.py:52,55: clean decode and noisy decode (x.detach() + noise_encoding) -- batched as one [2B] pass
+        mel2, post2 = self.decode(self._xx, out_len.repeat(2))
+        self._xx = None
+        mel, mel_n, post_mel, post_mel_n = mel2[:B], mel2[B:], post2[:B], post2[B:]
         ar = torch.arange(L, device=dev)
         src_mask = ar.unsqueeze(0) >= src_len.unsqueeze(1)
         mel_mask = torch.arange(T, device=dev).unsqueeze(0) >= out_len.unsqueeze(1)

@@ -238,13 +238,15 @@ def length_regulator_scan(duration):
 
 
 def bucket_embed_sum(text, spk, noise, p_val, e_val, p_scale, e_scale, pitch_bins, energy_bins, pitch_emb, energy_emb,
-                     want_noisy=True, want_idx=False):
+                     want_noisy=True, want_idx=False, out=None, out_noisy=None):
     text, in_bs, in_ld = _v3(text, "text")
     spk3, s_bs, s_ld = _v3(spk, "spk")
     assert (s_bs, s_ld) == (in_bs, in_ld), "text/spk/noise must share strides (slices of one expanded buffer)"
     B, T, C = text.shape
-    out = torch.empty(B, T, C, device=text.device, dtype=text.dtype)
-    out_n = torch.empty_like(out) if want_noisy else None
+    if out is None:
+        out = torch.empty(B, T, C, device=text.device, dtype=text.dtype)
+    out_n = (out_noisy if out_noisy is not None else torch.empty_like(out)) if want_noisy else None
+    assert out.is_contiguous() and (out_n is None or out_n.is_contiguous())
     p_idx = torch.empty(B, T, device=text.device, dtype=torch.int32) if want_idx else None
     e_idx = torch.empty(B, T, device=text.device, dtype=torch.int32) if want_idx else None
     assert p_val.is_contiguous() and e_val.is_contiguous() and p_val.dtype == torch.float32
