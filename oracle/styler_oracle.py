@@ -331,6 +331,23 @@ def style_modeling(sd, src_seq, speaker_embed, mel_target, mel_aug, p_norm, e_in
     return res
 
 
+def predict_inference(sd, text_encoding, pitch_encoding, energy_encoding, duration_encoding, speaker_encoding,
+                      noise_encoding, src_mask, max_len, speaker_normalized=True, d_control=1.0, p_control=1.0,
+                      e_control=1.0):
+    """modules.py:285-309 (StyleModeling.predict_inference, used by synthesize.py:171)."""
+    P = "style_modeling."
+    enc = torch.cat((text_encoding, pitch_encoding, speaker_encoding, energy_encoding, noise_encoding), dim=-1)
+    log_d = style_predictor(sd, P + "duration_predictor.", duration_encoding, src_mask)
+    enc, mel_len = length_regulator(enc, duration_from_log(log_d, d_control), max_len)
+    mel_mask = mask_from_lengths(mel_len)
+    text_T, pitch_T, spk_T, energy_T, noise_T = torch.split(enc, 256, dim=-1)
+    e_pred = style_predictor(sd, P + "energy_predictor.", energy_T, mel_mask) * e_control
+    e_emb = F.embedding(torch.bucketize(e_pred, sd[P + "energy_bins"]), sd[P + "energy_embedding.weight"])
+    p_pred = style_predictor(sd, P + "pitch_predictor.", pitch_T if speaker_normalized else pitch_T + spk_T, mel_mask) * p_control
+    p_emb = F.embedding(torch.bucketize(p_pred, sd[P + "pitch_bins"]), sd[P + "pitch_embedding.weight"])
+    return text_T, p_emb, spk_T, e_emb, noise_T, log_d, p_pred, e_pred, mel_mask
+
+
 def styler_forward(sd, src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target=None,
                    p_target=None, e_target=None, max_src_len=None, max_mel_len=None, speaker_embed=None,
                    d_control=1.0, p_control=1.0, e_control=1.0):

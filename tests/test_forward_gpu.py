@@ -127,3 +127,79 @@ def test_no_cpu_fallback():
     m = STYLER().eval()
     with pytest.raises(RuntimeError):
         m(*[torch.zeros(1, 4, dtype=torch.long)] * 7)
+
+
+def test_fftblock_config2_geometry(cuda):
+    """BASELINE configs[1]: one FFTBlock, B=16, L=128, fp32 (ragged key mask) -- tensor-core tf32 and CUDA-core fp32."""
+    from styler_b200.engine import Engine
+    sd = so.make_state_dict(2)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(16, 128, 256, generator=g)
+    lens = torch.randint(64, 129, (16,), generator=g)
+    lens[0] = 128
+    mask = so.mask_from_lengths(lens, 128)
+    x = x.masked_fill(mask.unsqueeze(-1), 0)
+    p = "decoder.layer_stack.2."
+    with torch.no_grad():
+        ref = so.fft_block(sd, p, x, mask)
+    for precision, tol in (("fp32", 2e-5), ("tf32", 1e-3), ("bf16", 2e-2)):
+        eng = Engine(sd, cuda, precision)
+        got = eng.fft_block(x.to(cuda, eng.dt), lens.to(cuda), eng.w.dec_layers[2])
+        torch.cuda.synchronize()
+        assert rel(got, ref) < tol, (precision, rel(got, ref))
+        assert torch.equal(got.float().cpu()[mask], torch.zeros_like(ref[mask]))      # padded rows exactly zero
+
+
+def test_predict_inference_and_submodule_entry_points(cuda):
+    """The sub-forward surface callers reach into (synthesize.py:116-128,170-205; train.py:149-153):
+    style_encoder.encoder_input_cat -> audio_encoder, and StyleModeling.predict_inference -> decode."""
+    from styler_b200 import STYLER
+    sd = so.make_state_dict(0)
+    so.set_duration_bias(sd, 4)
+    batch = so.make_inputs(B=2, L=24, Tr=70, seed=31, ragged=True, d_mode=None)
+    model = STYLER(precision="fp32")
+    model.load_state_dict(sd)
+    model = model.to(cuda).eval()
+    out = run(model, batch, cuda)
+    sm = model.style_modeling
+    # audio encoder entry point against the oracle
+    cat = sm.style_encoder.encoder_input_cat(batch["mel_target"].to(cuda), batch["p_norm"].to(cuda), batch["e_input"].to(cuda),
+                                             batch["mel_aug"].to(cuda))
+    d_enc, p_enc, e_enc, n_enc = sm.style_encoder.audio_encoder(cat, batch["mel_len"].to(cuda), batch["src_len"].to(cuda), mask=None)
+    with torch.no_grad():
+        ref_cat = so.encoder_input_cat(batch["mel_target"], batch["p_norm"], batch["e_input"], batch["mel_aug"])
+        r_d, r_p, r_e, r_n = so.audio_encoder(sd, "style_modeling.style_encoder.audio_encoder.", ref_cat, batch["mel_len"],
+                                              batch["src_len"])
+    for got, ref in ((d_enc, r_d), (p_enc, r_p), (e_enc, r_e), (n_enc, r_n)):
+        assert rel(got, ref) < 1e-4
+    # predict_inference with the stored inspection tensors (synthesize.py:170-172) reproduces the forward's mels
+    enc = [t.float().cpu() for t in (sm.text_encoding, sm.pitch_encoding, sm.energy_encoding, sm.duration_encoding,
+                                     sm.speaker_encoding, sm.noise_encoding, sm.text_encoding_neck, sm.speaker_encoding_p)]
+    text, p_raw, e_up, d_up, spk, n_up, neck, spk_p = enc
+    with torch.no_grad():
+        p_up = so._mlp2(sd, "style_modeling.pitch_linear.", p_raw + spk_p)
+        ref_pi = so.predict_inference(sd, text, neck + p_up, neck + e_up, neck + d_up, spk, n_up, out["src_mask"].cpu(), None,
+                                      speaker_normalized=False)
+    got_pi = sm.predict_inference(text.to(cuda), (neck + p_up).to(cuda), (neck + e_up).to(cuda), (neck + d_up).to(cuda),
+                                  spk.to(cuda), n_up.to(cuda), out["src_mask"], None, speaker_normalized=False)
+    assert torch.equal(got_pi[8].cpu(), ref_pi[8])
+    for i in (0, 1, 2, 3, 4, 5, 6, 7):
+        assert rel(got_pi[i], ref_pi[i]) < 1e-4, i
+    x = got_pi[0].float() + got_pi[1].float() + got_pi[2].float() + got_pi[3].float()
+    mel, post = model.decode(x, got_pi[8])
+    assert rel(mel, out["mel"]) < 1e-4 and rel(post, out["mel_postnet"]) < 1e-4
+
+
+def test_data_parallel_shards_match_single_gpu(cuda):
+    """sharding the batch by utterance with the global padded lengths is bitwise identical to one batch."""
+    from styler_b200 import STYLER
+    from styler_b200 import dist as sdist
+    sd = so.make_state_dict(0)
+    batch = so.make_inputs(B=4, L=32, seed=41, ragged=True, d_mode="ragged")
+    model = STYLER(precision="bf16")
+    model.load_state_dict(sd)
+    model = model.to(cuda).eval()
+    full = run(model, batch, cuda)
+    parts = [run(model, sdist.shard_batch(batch, r, 2), cuda) for r in range(2)]
+    for k in ("mel", "mel_postnet_noisy", "log_d", "p_pred"):
+        assert torch.equal(torch.cat([p[k] for p in parts], 0), full[k]), k
