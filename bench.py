@@ -215,15 +215,19 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     frames_per_step = int(host[0]["mel_len"].sum().item())
 
+    gatherer = sdist.AsyncGather(dev) if world > 1 else None
+
     def step(bt):
         out = model(bt["src_seq"], bt["mel_target"], bt["mel_aug"], bt["p_norm"], bt["e_input"], bt["src_len"],
                     bt["mel_len"], d_target=bt["d_target"], p_target=bt["p_target"], e_target=bt["e_target"],
                     max_src_len=L, max_mel_len=T, speaker_embed=bt["speaker_embed"])
-        if world > 1:
-            sdist.gather_to_rank0([out[0][0], out[0][1], out[1][0], out[1][1], out[7]])
+        if gatherer is not None:   # NCCL gather of the 4 mels + lengths to rank 0 on the comm stream (overlaps the next step)
+            gatherer.launch([out[0][0], out[0][1], out[1][0], out[1][1], out[7]])
         return out
 
     def barrier():
+        if gatherer is not None:
+            gatherer.wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -277,24 +281,49 @@ def main():
                 "flops_per_launch": flops, "traffic": traffic}
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------
-    d2h_bufs = [torch.empty(B_PER_GPU, T, 80, dtype=torch.float32).pin_memory() for _ in range(2)]
-    len_buf = torch.empty(B_PER_GPU, dtype=torch.int64).pin_memory()
+    # Two user streams alternate (each with its own pinned result buffers): step i's H2D / D2H copies overlap step
+    # i+-1's kernels, as a serving loop would drive the public API.  Every step still does its own H2D of all inputs and
+    # D2H of its results inside the timed region.
+    e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    d2h = [[torch.empty(B_PER_GPU, T, 80, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
+    len_buf = [torch.empty(B_PER_GPU, dtype=torch.int64).pin_memory() for _ in range(2)]
 
     def e2e_step(i):
-        hb = host[i % NBUF]
-        bt = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        out = step(bt)
-        d2h_bufs[0].copy_(out[1][0], non_blocking=True)
-        d2h_bufs[1].copy_(out[1][1], non_blocking=True)
-        len_buf.copy_(out[7], non_blocking=True)
+        k = i % 2
+        with torch.cuda.stream(e2e_streams[k]):
+            hb = host[i % NBUF]
+            bt = {kk: v.to(dev, non_blocking=True) for kk, v in hb.items()}
+            out = step(bt)
+            d2h[k][0].copy_(out[1][0], non_blocking=True)
+            d2h[k][1].copy_(out[1][1], non_blocking=True)
+            len_buf[k].copy_(out[7], non_blocking=True)
+
+    def e2e_timed(steps):
+        barrier()
+        for st in e2e_streams:
+            st.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            e2e_step(i)
+        for st in e2e_streams:
+            st.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([wall], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt.item()
 
     e2e_step(0)
-    e2e_secs, e2e_wall = timed(e2e_step, args.steps)
-    e2e_secs = max(e2e_secs, e2e_wall if world == 1 else e2e_secs)
+    e2e_step(1)
+    e2e_secs = e2e_timed(args.steps)
     e2e_value = world * frames_per_step * args.steps / e2e_secs
-    d2h_bytes = 2 * d2h_bufs[0].numel() * 4 + len_buf.numel() * 8
+    d2h_bytes = 2 * d2h[0][0].numel() * 4 + len_buf[0].numel() * 8
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -315,6 +344,9 @@ def main():
                 "ms_per_step": 1e3 * e2e_secs / args.steps},
         "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
         "wall_s_timed_region": wall}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

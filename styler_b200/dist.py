@@ -52,3 +52,43 @@ def gather_to_rank0(tensors, dst=0):
         dist.gather(t, bufs, dst=dst)
         outs.append(torch.cat(bufs, dim=0) if rank == dst else None)
     return outs
+
+
+class AsyncGather:
+    """Gather of the per-rank mel tensors to rank 0 on a dedicated communication stream, so the NVLink transfer of
+    step i overlaps the compute of step i+1 (the transfer is 84 MB per rank per step at config 3).  Receive buffers
+    on rank 0 are allocated once and reused.  `wait()` joins the communication stream into the current stream."""
+
+    def __init__(self, device, dst=0):
+        self.device, self.dst = device, dst
+        self.stream = torch.cuda.Stream(device=device)
+        self._bufs = {}
+        self.result = None
+
+    def launch(self, tensors):
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            self.result = list(tensors)
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.stream.wait_event(ready)
+        outs = []
+        with torch.cuda.stream(self.stream):
+            for i, t in enumerate(tensors):
+                t = t.contiguous()
+                t.record_stream(self.stream)
+                bufs = None
+                if rank == self.dst:
+                    key = (i, tuple(t.shape), t.dtype)
+                    if key not in self._bufs:
+                        self._bufs[key] = [torch.empty_like(t) for _ in range(world)]
+                    bufs = self._bufs[key]
+                dist.gather(t, bufs, dst=self.dst)
+                outs.append(bufs)
+        self.result = outs
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self.result
