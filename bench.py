@@ -197,7 +197,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from oracle import styler_oracle as so        # seeded synthetic weights/inputs only (generators, not compute)
+    from styler_b200 import synthetic as so      # seeded synthetic weights/inputs (no oracle import on the GPU arm)
     from styler_b200 import STYLER, _lib
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)

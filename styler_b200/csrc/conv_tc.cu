@@ -493,7 +493,12 @@ int pick_bn(const styler_conv1d_args& a, int m_tiles) {
     for (int bn = 256; bn >= 16; bn -= 16) {
       if (a.N % bn != 0) continue;
       if (a.vt != nullptr && a.vt_col0 % bn != 0) continue;
-      if (pass == 0 && ((bn * es) % 128 != 0 || a.out == nullptr)) continue;
+      if (pass == 0) {   // coalesced-epilogue candidates: whole boxes and a tile that fits the pipeline smem
+        const int sb = kAStageBytes + bn * 128;
+        int st = smem_budget_bytes() / sb;
+        st = st > 8 ? 8 : (st < 2 ? 2 : st);
+        if ((bn * es) % 128 != 0 || a.out == nullptr || static_cast<long long>(bn) * es * 128 > static_cast<long long>(st) * sb) continue;
+      }
       if (largest == 0) largest = bn;
       if (static_cast<long long>(m_tiles) * (a.N / bn) >= 296) return bn;
       if (bn >= 64) smallest64 = bn;

@@ -2,7 +2,7 @@
 // The reference evaluates a dense 1026x1024 DFT as a strided Conv1d (2.1 MFLOP/frame) and bounces through
 // the host; here one CTA handles 8 consecutive frames of one utterance:
 //   stage the 8*256+768 reflect-padded samples in smem once (the 4x frame overlap is served from smem),
-//   periodic-Hann window, 1024-point real FFT as a 512-point complex Stockham radix-2 FFT + split post-pass
+//   periodic-Hann window, 1024-point real FFT as a 512-point complex Stockham FFT (4 radix-4 + 1 radix-2 passes) + split post-pass
 //   (64 threads per frame, 4 frames in flight), magnitude for the 513 bins -> smem,
 //   energy = ||mag||_2, mel = log(max(basis @ mag, 1e-5)) using the non-zero band of each filter row.
 // Bounding roofline: HBM (464,580 algorithmic bytes per 4 s utterance); the FFT stage is smem/ALU work.
@@ -38,11 +38,22 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
   float* samp = reinterpret_cast<float*>(mag + FPB);                                      // [NSAMP]
   const int b = blockIdx.y, f0 = blockIdx.x * FPB;
   const float* yb = y + static_cast<long long>(b) * N;
-  for (int i = threadIdx.x; i < NSAMP; i += 256) {
-    int src = f0 * HOP + i - NFFT / 2;         // reflect padding (F.pad mode='reflect', stft.py:58-62)
-    if (src < 0) src = -src;
-    if (src >= N) src = 2 * (N - 1) - src;
-    samp[i] = (src >= 0 && src < N) ? yb[src] : 0.f;
+  {   // all loads of the window are issued before the first store (11 independent global loads in flight per thread)
+    constexpr int kIter = (NSAMP + 255) / 256;
+    float v[kIter];
+#pragma unroll
+    for (int j = 0; j < kIter; ++j) {
+      const int i = threadIdx.x + j * 256;
+      int src = f0 * HOP + i - NFFT / 2;         // reflect padding (F.pad mode='reflect', stft.py:58-62)
+      if (src < 0) src = -src;
+      if (src >= N) src = 2 * (N - 1) - src;
+      v[j] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kIter; ++j) {
+      const int i = threadIdx.x + j * 256;
+      if (i < NSAMP) samp[i] = v[j];
+    }
   }
   for (int k = threadIdx.x; k < HALF; k += 256) {
     float s, c;
@@ -64,23 +75,50 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
       const float w0 = 0.5f - 0.5f * c0, w1 = 0.5f - 0.5f * c1;
       d0[n] = make_float2(samp[fl * HOP + i0] * w0, samp[fl * HOP + i1] * w1);
     }
-    __syncthreads();
-    // 512-point Stockham radix-2: 9 passes, 256 butterflies each
+    // 512-point Stockham FFT: four radix-4 passes (Ns = 1, 4, 16, 64; 128 butterflies each, 2 per thread) and one radix-2
+    // pass (Ns = 256).  Only the 64 threads of this frame group synchronise (named barrier 1+grp), not the whole CTA.
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory"); };
+    auto cmul = [](float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); };
+    group_sync();
 #pragma unroll 1
-    for (int s = 0; s < 9; ++s) {
-      const int Ns = 1 << s;
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int Ns = 1 << (2 * s4);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int jdx = lt + q * 64;
+      for (int qq = 0; qq < 2; ++qq) {
+        const int jdx = lt + qq * 64;                 // 0..127
+        const int k = jdx & (Ns - 1);
+        // twiddles exp(-2*pi*i*r*k/(4*Ns)) = W_1024^(r*k*256/Ns), r = 1..3 (index < 768: fold with W^(512+m) = -W^m)
+        const int tstep = k * (256 / Ns);
+        float2 v0 = d0[jdx], v1 = d0[jdx + 128], v2 = d0[jdx + 256], v3 = d0[jdx + 384];
+        const float2 w1 = tw[tstep], w2 = tw[2 * tstep];
+        const int t3 = 3 * tstep;
+        const float2 w3 = t3 < HALF ? tw[t3] : make_float2(-tw[t3 - HALF].x, -tw[t3 - HALF].y);
+        v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
+        // radix-4 butterfly (forward transform: -i rotation)
+        const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y), a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+        const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y), a3 = make_float2(v1.x - v3.x, v1.y - v3.y);
+        const int dst = ((jdx - k) << 2) + k;
+        d1[dst] = make_float2(a0.x + a2.x, a0.y + a2.y);
+        d1[dst + Ns] = make_float2(a1.x + a3.y, a1.y - a3.x);
+        d1[dst + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+        d1[dst + 3 * Ns] = make_float2(a1.x - a3.y, a1.y + a3.x);
+      }
+      group_sync();
+      float2* tmp = d0; d0 = d1; d1 = tmp;
+    }
+    {
+      const int Ns = 256;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int jdx = lt + qq * 64;                 // 0..255
         const int k = jdx & (Ns - 1);
         const float2 w = tw[k * (HALF / Ns)];
-        const float2 a = d0[jdx], bb = d0[jdx + 256];
-        const float2 bw = make_float2(bb.x * w.x - bb.y * w.y, bb.x * w.y + bb.y * w.x);
+        const float2 a = d0[jdx], bw = cmul(d0[jdx + 256], w);
         const int dst = ((jdx - k) << 1) + k;
         d1[dst] = make_float2(a.x + bw.x, a.y + bw.y);
         d1[dst + Ns] = make_float2(a.x - bw.x, a.y - bw.y);
       }
-      __syncthreads();
+      group_sync();
       float2* tmp = d0; d0 = d1; d1 = tmp;
     }
     // split post-pass: X[k] = E + W^k * O, k = 0..512
@@ -96,8 +134,9 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
       const float xi = e.y + (o.x * w.y + o.y * w.x);
       mag[fl][k] = sqrtf(xr * xr + xi * xi);
     }
-    __syncthreads();
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");   // the group's buffers are reused by its next frame
   }
+  __syncthreads();
 
   // energy: L2 norm over the 513 bins (stft.py:158); warp per frame
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
