@@ -1,5 +1,6 @@
 // C-ABI plumbing: version, thread-local error string, launch counter, TMA descriptor cache.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -13,6 +14,12 @@ namespace sb {
 
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("STYLER_PDL"); v = (e != nullptr && atoi(e) != 0) ? 1 : 0; }   // off by default: measured 8.71 ms/step with PDL vs 8.07 without
+  return v == 1;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(kThreadsTc) attention_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  pdl_launch_dependents();
+  pdl_grid_dependency_wait();     // the QKV projection (previous kernel) is complete and visible from here on
 
   if (warp == 0) {
     if (lane == 0 && nkt > 0) {
@@ -352,8 +354,8 @@ int launch_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t 
     attr_set = true;
   }
   const int q_tiles = ceil_div(Tlen, kQ);
-  kern<<<B * H * q_tiles, kThreadsTc, C::smem, s>>>(tmQK, tmVT, lens, static_cast<T*>(ctx), ctx_bs, ctx_ld, Tlen, H,
-                                                    q_tiles, v_mn);
+  SB_CUDA_OK(launch_pdl(kern, dim3(B * H * q_tiles), dim3(kThreadsTc), C::smem, s, tmQK, tmVT, lens, static_cast<T*>(ctx),
+                        static_cast<long long>(ctx_bs), ctx_ld, Tlen, H, q_tiles, v_mn));
   SB_LAUNCH_OK();
   return 0;
 }

@@ -98,6 +98,25 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Launch with programmatic stream serialization (PDL): the kernel must call pdl_grid_dependency_wait() before it reads
+// anything a previous kernel wrote.  Opt-in with STYLER_PDL=1 (it measured slower on the full forward: the early CTAs of
+// the next kernel hold smem/TMEM slots while they wait).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // dispatch on the ABI dtype code

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();        // the next kernel may start its prologue in SM slots this grid no longer needs
+  pdl_grid_dependency_wait();     // everything above overlapped the previous kernel's tail; its outputs are visible now
   if (dbg != nullptr && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -598,8 +600,8 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
     SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[ia][il][ifast] = true;
   }
-  kern<<<m_tiles * n_tiles, kThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles, tiles_per_utt, a.KS, a.pad,
-                                                      kb_per_tap, BN, stages);
+  SB_CUDA_OK(launch_pdl(kern, dim3(m_tiles * n_tiles), dim3(kThreads), smem, stream, tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles,
+                        tiles_per_utt, a.KS, a.pad, kb_per_tap, BN, stages));
   SB_LAUNCH_OK();
   return 0;
 }

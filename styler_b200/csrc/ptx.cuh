@@ -53,6 +53,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream (launched with programmaticStreamSerializationAllowed) may start
+// occupying SM resources as they free up; grid_dependency_wait: block until the previous kernel has fully completed and
+// its writes are visible.  Everything before the wait (barrier init, TMEM alloc, descriptor prefetch, parameter staging of
+// constant weights) overlaps the previous kernel's tail wave.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxy / tcgen05 fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
