@@ -2,13 +2,16 @@
 and the TacotronSTFT mel front end, behind the reference's Python surface.  See DESIGN.md / INTEGRATION.md."""
 from . import _lib  # noqa: F401
 
-__all__ = ["STYLER", "TacotronSTFT", "ops", "hparams"]
+__all__ = ["STYLER", "GraphedSTYLER", "TacotronSTFT", "ops", "hparams"]
 
 
 def __getattr__(name):
     if name == "STYLER":
         from .model import STYLER
         return STYLER
+    if name == "GraphedSTYLER":
+        from .model import GraphedSTYLER
+        return GraphedSTYLER
     if name == "TacotronSTFT":
         from .stft import TacotronSTFT
         return TacotronSTFT

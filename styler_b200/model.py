@@ -161,7 +161,37 @@ def _mlp(i, h):
     return nn.Sequential(nn.Linear(i, h), nn.ReLU(), nn.Linear(h, h), nn.ReLU())
 
 
+class _Inspection:
+    """Inspection tensor left on StyleModeling by forward() (modules.py:328-331,342-348).  The engine keeps it in the
+    activation dtype; callers (synthesize.py:114-144,180-205) feed it to fp32 torch sub-modules, so it is exposed as fp32,
+    converted lazily on first access (nothing is converted on the forward hot path).  Assignable like a plain attribute."""
+
+    def __init__(self, name):
+        self.slot = "_insp_" + name
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        v = obj.__dict__.get(self.slot)
+        if torch.is_tensor(v) and v.dtype != torch.float32:
+            v = v.float()
+            obj.__dict__[self.slot] = v
+        return v
+
+    def __set__(self, obj, value):
+        obj.__dict__[self.slot] = value
+
+
 class StyleModeling(_Container):            # modules.py:238-283
+    pitch_encoding = _Inspection("pitch_encoding")
+    speaker_encoding = _Inspection("speaker_encoding")
+    speaker_encoding_p = _Inspection("speaker_encoding_p")
+    text_encoding_neck = _Inspection("text_encoding_neck")
+    duration_encoding = _Inspection("duration_encoding")
+    energy_encoding = _Inspection("energy_encoding")
+    noise_encoding = _Inspection("noise_encoding")
+    text_encoding = _Inspection("text_encoding")
+
     def __init__(self, owner):
         super().__init__()
         object.__setattr__(self, "_owner", owner)
@@ -297,3 +327,49 @@ class STYLER(nn.Module):
                           max_src_len, max_mel_len, speaker_embed, d_control, p_control, e_control)
         self.style_modeling._store_inspection(eng, out[5], max_mel_len)
         return out
+
+
+class GraphedSTYLER:
+    """CUDA-graph replay of one forward geometry (shapes, teacher forcing and padded lengths fixed).
+
+    The 130-odd kernel launches of a forward (plus the side-stream fork/join of the audio-encoder branches) are
+    captured once into a CUDA graph; `__call__` copies the new inputs into the captured static buffers and replays the
+    graph with a single launch, which removes the per-launch host cost that dominates small batches (single-utterance
+    latency).  Requirements: teacher-forced durations or an explicit `max_mel_len` (the free-running branch needs one
+    host read of max(mel_len), styler.py:47-49 / modules.py:360, which cannot be captured) -- for free-running inference
+    capture with the `max_mel_len` you are willing to pad to.
+    """
+
+    def __init__(self, model, example_args, example_kwargs, warmup=2):
+        self.model = model
+        eng = model._engine_for()
+        dev = eng.device
+        if example_kwargs.get("d_target") is None and not example_kwargs.get("max_mel_len"):
+            raise ValueError("GraphedSTYLER needs d_target or max_mel_len (no host sync may happen inside a CUDA graph)")
+        self.static_args = [a.to(dev).clone() if torch.is_tensor(a) else a for a in example_args]
+        self.static_kwargs = {k: (v.to(dev).clone() if torch.is_tensor(v) else v) for k, v in example_kwargs.items()}
+        T = self.static_kwargs.get("max_mel_len") or int(self.static_kwargs["d_target"].sum(1).max().item())
+        self.static_kwargs["max_mel_len"] = T
+        eng._pos("dec", T)                                   # position tables beyond max_seq_len are built on the host: do it now
+        eng._pos("enc", self.static_args[0].shape[1])
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                model(*self.static_args, **self.static_kwargs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = model(*self.static_args, **self.static_kwargs)
+
+    def __call__(self, *args, **kwargs):
+        for dst, src in zip(self.static_args, args):
+            if torch.is_tensor(dst):
+                dst.copy_(src, non_blocking=True)
+        for k, v in kwargs.items():
+            dst = self.static_kwargs.get(k)
+            if torch.is_tensor(dst):
+                dst.copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
