@@ -41,24 +41,39 @@ __global__ void __launch_bounds__(4 * H) bilstm_kernel(const float* __restrict__
     for (int nb = 0; nb < NB; ++nb) gnext[nb] = gx_at(nb, step + 1);
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
-      float acc0 = gcur[nb], acc1 = 0.f;
+      // four independent accumulation chains (the H-long dependent FMA chain was the per-step critical path)
+      float acc0 = gcur[nb], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
       const float4* h4 = reinterpret_cast<const float4*>(&hs[nb][0]);
 #pragma unroll
       for (int k = 0; k < H / 4; ++k) {
         const float4 hv = h4[k];
         acc0 = fmaf(w[4 * k], hv.x, acc0);
         acc1 = fmaf(w[4 * k + 1], hv.y, acc1);
-        acc0 = fmaf(w[4 * k + 2], hv.z, acc0);
-        acc1 = fmaf(w[4 * k + 3], hv.w, acc1);
+        acc2 = fmaf(w[4 * k + 2], hv.z, acc2);
+        acc3 = fmaf(w[4 * k + 3], hv.w, acc3);
       }
-      gs[nb][j] = acc0 + acc1;
+      gs[nb][j] = (acc0 + acc1) + (acc2 + acc3);
     }
     __syncthreads();
     if (j < NB * H && b0 + my_nb < B) {
       const float gi = gs[my_nb][my_k], gf = gs[my_nb][H + my_k], gg = gs[my_nb][2 * H + my_k], go = gs[my_nb][3 * H + my_k];
-      const float i_ = 1.f / (1.f + expf(-gi)), f_ = 1.f / (1.f + expf(-gf)), o_ = 1.f / (1.f + expf(-go));
-      c = f_ * c + i_ * tanhf(gg);
-      const float h = o_ * tanhf(c);
+      float i_, f_, o_, g_, h;
+      if constexpr (sizeof(T) == 2) {
+        // bf16 activations: MUFU.TANH based gates (rel. error 2^-11, far below the bf16 rounding of h); the fp32 modes
+        // keep the accurate expf/tanhf forms
+        auto tanh_fast = [](float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+        i_ = fmaf(0.5f, tanh_fast(0.5f * gi), 0.5f);
+        f_ = fmaf(0.5f, tanh_fast(0.5f * gf), 0.5f);
+        o_ = fmaf(0.5f, tanh_fast(0.5f * go), 0.5f);
+        g_ = tanh_fast(gg);
+        c = f_ * c + i_ * g_;
+        h = o_ * tanh_fast(c);
+      } else {
+        i_ = 1.f / (1.f + expf(-gi)); f_ = 1.f / (1.f + expf(-gf)); o_ = 1.f / (1.f + expf(-go));
+        g_ = tanhf(gg);
+        c = f_ * c + i_ * g_;
+        h = o_ * tanhf(c);
+      }
       hs[my_nb][my_k] = h;
       const int t = dir ? L - 1 - step : step;
       DT<T>::st(out + (b0 + my_nb) * o_bs + static_cast<long long>(t) * o_ld + dir * H + my_k, h);

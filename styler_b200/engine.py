@@ -50,7 +50,8 @@ class Engine:
         self.inter = {}
         self.v_rowmajor = precision == "bf16"   # attention reads V row-major from the fused QKV buffer (MN-major B operand;
                                                # validated for kind::f16 only -- the fp32 modes keep the transposed-V layout)
-        self.use_streams = True   # run the four audio-encoder branches on side streams
+        import os
+        self.use_streams = os.environ.get("STYLER_NO_STREAMS", "0") != "1"   # four audio-encoder branches on side streams
         self._streams = None
         self.prof = None   # bench.py: list collecting (start_event, end_event, B, T) around the dominant kernel (FFN conv k9)
         self._pack({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
