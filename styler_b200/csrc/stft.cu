@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
   float2* tw = reinterpret_cast<float2*>(stft_smem + sizeof(float2) * 4 * 2 * HALF);      // W_1024^k, k < 512
   float (*mag)[NBINS + 3] = reinterpret_cast<float (*)[NBINS + 3]>(tw + HALF);            // [FPB][516]
   float* samp = reinterpret_cast<float*>(mag + FPB);                                      // [NSAMP]
+  float* hann = samp + NSAMP;                                                             // [NFFT] periodic Hann
   const int b = blockIdx.y, f0 = blockIdx.x * FPB;
   const float* yb = y + static_cast<long long>(b) * N;
   {   // all loads of the window are issued before the first store (11 independent global loads in flight per thread)
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
     float s, c;
     sincospif(-static_cast<float>(k) / 512.0f, &s, &c);
     tw[k] = make_float2(c, s);
+    hann[k] = 0.5f - 0.5f * c;                 // cos(2*pi*k/1024) = Re W^k ;  cos(2*pi*(k+512)/1024) = -Re W^k
+    hann[k + HALF] = 0.5f + 0.5f * c;
   }
   __syncthreads();
 
@@ -68,12 +71,14 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
     float2* d0 = buf[grp][0];
     float2* d1 = buf[grp][1];
     // window + pack real pairs into complex: z[n] = x[2n] + i x[2n+1]
-    for (int n = lt; n < HALF; n += 64) {
-      const int i0 = 2 * n, i1 = 2 * n + 1;
-      const float c0 = i0 < HALF ? tw[i0].x : -tw[i0 - HALF].x;   // cos(2*pi*i/1024)
-      const float c1 = i1 < HALF ? tw[i1].x : -tw[i1 - HALF].x;
-      const float w0 = 0.5f - 0.5f * c0, w1 = 0.5f - 0.5f * c1;
-      d0[n] = make_float2(samp[fl * HOP + i0] * w0, samp[fl * HOP + i1] * w1);
+    {
+      const float2* sp = reinterpret_cast<const float2*>(samp + fl * HOP);   // fl*HOP is even -> 8-byte aligned
+      const float2* hp2 = reinterpret_cast<const float2*>(hann);
+#pragma unroll
+      for (int n = lt; n < HALF; n += 64) {
+        const float2 x = sp[n], w = hp2[n];
+        d0[n] = make_float2(x.x * w.x, x.y * w.y);
+      }
     }
     // 512-point Stockham FFT: four radix-4 passes (Ns = 1, 4, 16, 64; 128 butterflies each, 2 per thread) and one radix-2
     // pass (Ns = 256).  Only the 64 threads of this frame group synchronise (named barrier 1+grp), not the whole CTA.
@@ -121,18 +126,19 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
       group_sync();
       float2* tmp = d0; d0 = d1; d1 = tmp;
     }
-    // split post-pass: X[k] = E + W^k * O, k = 0..512
-    for (int k = lt; k <= HALF; k += 64) {
+    // split post-pass: X[k] = E + W^k * O.  Bins k and 512-k share Z[k], Z[512-k] and the twiddle
+    // (E(512-k) = conj E(k), O(512-k) = conj O(k), W^(512-k) = -conj W^k), so each thread produces two magnitudes.
+    for (int k = lt; k <= HALF / 2; k += 64) {
       const float2 zk = d0[k & (HALF - 1)];
       const float2 zr = d0[(HALF - k) & (HALF - 1)];
-      const float2 zc = make_float2(zr.x, -zr.y);
-      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-      const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
-      const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);       // -i/2 * d
-      const float2 w = k < HALF ? tw[k] : make_float2(-1.f, 0.f);
-      const float xr = e.x + (o.x * w.x - o.y * w.y);
-      const float xi = e.y + (o.x * w.y + o.y * w.x);
+      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
+      const float2 o = make_float2(0.5f * (zk.y + zr.y), -0.5f * (zk.x - zr.x));        // -i/2 * (zk - conj(zr))
+      const float2 w = tw[k];
+      const float2 wo = make_float2(o.x * w.x - o.y * w.y, o.x * w.y + o.y * w.x);
+      const float xr = e.x + wo.x, xi = e.y + wo.y;                                      // X[k]
+      const float yr = e.x - wo.x, yi = -e.y + wo.y;                                     // X[512-k] = conj(E) - conj(W^k O)
       mag[fl][k] = sqrtf(xr * xr + xi * xi);
+      mag[fl][HALF - k] = sqrtf(yr * yr + yi * yi);
     }
     asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");   // the group's buffers are reused by its next frame
   }
@@ -172,7 +178,7 @@ extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const f
   SB_LAUNCH_OK();
   dim3 grid(ceil_div(F, FPB), B);
   constexpr size_t smem = sizeof(float2) * 4 * 2 * HALF + sizeof(float2) * HALF + sizeof(float) * FPB * (NBINS + 3) +
-                          sizeof(float) * NSAMP;
+                          sizeof(float) * NSAMP + sizeof(float) * NFFT;
   static bool attr_set = false;
   if (!attr_set) {
     SB_CUDA_OK(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
