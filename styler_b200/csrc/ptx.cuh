@@ -53,6 +53,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Latency-critical variant: plain try_wait (hardware-default suspend window, no long park), spun until the phase flips.
+// For barriers that sit on a short per-tile dependency chain (attention: S ready -> softmax -> P ready -> MMA), where the
+// wake-up latency of a parked warp would be paid twice per key tile.
+__device__ __forceinline__ uint32_t mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_nohint(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_nohint(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("styler_b200: mbarrier watchdog fired (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // launch_dependents: the next kernel in the stream (launched with programmaticStreamSerializationAllowed) may start
 // occupying SM resources as they free up; grid_dependency_wait: block until the previous kernel has fully completed and

@@ -1,18 +1,24 @@
 // TacotronSTFT.mel_spectrogram (audio/stft.py:51-79,141-160; audio_processing.py:80-86 of the reference).
 // The reference evaluates a dense 1026x1024 DFT as a strided Conv1d (2.1 MFLOP/frame) and bounces through
-// the host; here one CTA handles 8 consecutive frames of one utterance:
-//   stage the 8*256+768 reflect-padded samples in smem once (the 4x frame overlap is served from smem),
-//   periodic-Hann window, 1024-point real FFT as a 512-point complex Stockham FFT (4 radix-4 + 1 radix-2 passes) + split post-pass
-//   (64 threads per frame, 4 frames in flight), magnitude for the 513 bins -> smem,
-//   energy = ||mag||_2, mel = log(max(basis @ mag, 1e-5)) using the non-zero band of each filter row.
-// Bounding roofline: HBM (464,580 algorithmic bytes per 4 s utterance); the FFT stage is smem/ALU work.
+// the host; here one CTA handles 32 consecutive frames of one utterance, one frame per warp at a time:
+//   stage the 31*256+1024 reflect-padded samples in smem once (the 4x frame overlap is served from smem),
+//   periodic-Hann window, 1024-point real FFT as a 512-point complex Stockham FFT (three radix-8 passes, 16 points per
+//   lane in registers, warp-private smem exchange) + split post-pass, magnitude for the 513 bins,
+//   energy = ||mag||_2, mel = log(max(basis @ mag, 1e-5)) over the non-zero band of each filter row, staged in smem
+//   and stored as 128-byte runs.
+// Bounding roofline: HBM (464,580 algorithmic bytes per 4 s utterance); the FFT stage is ALU/smem work.
 #include "common.cuh"
 
 namespace sb {
 namespace {
 
-constexpr int NFFT = 1024, HOP = 256, NBINS = 513, FPB = 8, HALF = 512;
+constexpr int NFFT = 1024, HOP = 256, NBINS = 513, HALF = 512;
+constexpr int FPB = 32;                              // frames per CTA (one 128-byte run of every mel row)
+constexpr int kWarps = 8;                            // one frame per warp in flight, FPB / kWarps frames per warp
 constexpr int NSAMP = (FPB - 1) * HOP + NFFT;
+constexpr int WBUF = HALF + HALF / 16;               // complex work buffer per warp, skewed: slot(i) = i + (i >> 4)
+constexpr int MAGLD = NBINS + 3;
+constexpr int MELLD = FPB + 1;
 
 __global__ void mel_band_kernel(const float* __restrict__ basis, int n_mels, int32_t* __restrict__ band) {
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -28,140 +34,167 @@ __global__ void mel_band_kernel(const float* __restrict__ basis, int n_mels, int
   if (lane == 0) { band[2 * m] = hi >= 0 ? lo : 0; band[2 * m + 1] = hi >= 0 ? hi + 1 : 0; }
 }
 
-__global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__ y, int N, int F,
-                                                       const float* __restrict__ basis, const int32_t* __restrict__ band,
-                                                       int n_mels, float* __restrict__ mel, float* __restrict__ energy) {
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// 4-point forward DFT, natural order in and out
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), s3 = mul_mi(csub(a1, a3));
+  a0 = cadd(s0, s2); a1 = cadd(s1, s3); a2 = csub(s0, s2); a3 = csub(s1, s3);
+}
+// 8-point forward DFT in registers; v[] natural order in, natural order out
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  constexpr float kR = 0.70710678118654752f;
+  float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+  float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+  b1 = make_float2((b1.x + b1.y) * kR, (b1.y - b1.x) * kR);      // * (1 - i)/sqrt(2)
+  b2 = mul_mi(b2);
+  b3 = make_float2((b3.y - b3.x) * kR, -(b3.x + b3.y) * kR);     // * (-1 - i)/sqrt(2)
+  dft4(a0, a1, a2, a3);
+  dft4(b0, b1, b2, b3);
+  v[0] = a0; v[1] = b0; v[2] = a1; v[3] = b1; v[4] = a2; v[5] = b2; v[6] = a3; v[7] = b3;
+}
+
+// One warp = one frame: 512-point complex Stockham FFT as three radix-8 passes (Ns = 1, 8, 64), each lane owning two
+// 8-point butterflies per pass held in registers; the passes exchange data through a per-warp smem buffer, so the only
+// synchronisation inside the transform is __syncwarp().
+__global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* __restrict__ y, int N, int F,
+                                                                  const float* __restrict__ basis,
+                                                                  const int32_t* __restrict__ band, int n_mels,
+                                                                  float* __restrict__ mel, float* __restrict__ energy) {
   extern __shared__ __align__(16) uint8_t stft_smem[];
-  float2 (*buf)[2][HALF] = reinterpret_cast<float2 (*)[2][HALF]>(stft_smem);             // [4][2][512]
-  float2* tw = reinterpret_cast<float2*>(stft_smem + sizeof(float2) * 4 * 2 * HALF);      // W_1024^k, k < 512
-  float (*mag)[NBINS + 3] = reinterpret_cast<float (*)[NBINS + 3]>(tw + HALF);            // [FPB][516]
-  float* samp = reinterpret_cast<float*>(mag + FPB);                                      // [NSAMP]
-  float* hann = samp + NSAMP;                                                             // [NFFT] periodic Hann
+  float2* tw = reinterpret_cast<float2*>(stft_smem);                       // W_1024^k, k < 512
+  float2* wbuf = tw + HALF;                                                // [kWarps][WBUF]
+  float* hann = reinterpret_cast<float*>(wbuf + kWarps * WBUF);            // [NFFT] periodic Hann
+  float* samp = hann + NFFT;                                               // [NSAMP]
+  float* mag = samp + NSAMP;                                               // [kWarps][MAGLD]
+  float* s_en = mag + kWarps * MAGLD;                                      // [FPB]
+  float* s_mel = s_en + FPB;                                               // [n_mels][MELLD]
   const int b = blockIdx.y, f0 = blockIdx.x * FPB;
   const float* yb = y + static_cast<long long>(b) * N;
-  {   // all loads of the window are issued before the first store (11 independent global loads in flight per thread)
-    constexpr int kIter = (NSAMP + 255) / 256;
-    float v[kIter];
+  for (int i0 = 0; i0 < NSAMP; i0 += 4 * kWarps * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
+    float v[4];
 #pragma unroll
-    for (int j = 0; j < kIter; ++j) {
-      const int i = threadIdx.x + j * 256;
-      int src = f0 * HOP + i - NFFT / 2;         // reflect padding (F.pad mode='reflect', stft.py:58-62)
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kWarps * 32 + threadIdx.x;
+      int src = f0 * HOP + i - NFFT / 2;
       if (src < 0) src = -src;
       if (src >= N) src = 2 * (N - 1) - src;
-      v[j] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
+      v[u] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < kIter; ++j) {
-      const int i = threadIdx.x + j * 256;
-      if (i < NSAMP) samp[i] = v[j];
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kWarps * 32 + threadIdx.x;
+      if (i < NSAMP) samp[i] = v[u];
     }
   }
-  for (int k = threadIdx.x; k < HALF; k += 256) {
-    float s, c;
-    sincospif(-static_cast<float>(k) / 512.0f, &s, &c);
-    tw[k] = make_float2(c, s);
-    hann[k] = 0.5f - 0.5f * c;                 // cos(2*pi*k/1024) = Re W^k ;  cos(2*pi*(k+512)/1024) = -Re W^k
-    hann[k + HALF] = 0.5f + 0.5f * c;
+  for (int k = threadIdx.x; k < HALF; k += kWarps * 32) {
+    float sn, cs;
+    sincospif(-static_cast<float>(k) / 512.0f, &sn, &cs);
+    tw[k] = make_float2(cs, sn);
+    hann[k] = 0.5f - 0.5f * cs;                 // cos(2*pi*k/1024) = Re W^k ;  cos(2*pi*(k+512)/1024) = -Re W^k
+    hann[k + HALF] = 0.5f + 0.5f * cs;
   }
   __syncthreads();
 
-  const int grp = threadIdx.x >> 6, lt = threadIdx.x & 63;   // 4 frames in flight, 64 threads each
-  for (int round = 0; round < FPB / 4; ++round) {
-    const int fl = round * 4 + grp;                          // local frame index
-    float2* d0 = buf[grp][0];
-    float2* d1 = buf[grp][1];
-    // window + pack real pairs into complex: z[n] = x[2n] + i x[2n+1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* wb = wbuf + warp * WBUF;
+  float* mg = mag + warp * MAGLD;
+  auto slot = [](int i) { return i + (i >> 4); };
+  auto twd = [&](int m) {                       // W_1024^m for m < 1024
+    const float2 w = tw[m & (HALF - 1)];
+    return m < HALF ? w : make_float2(-w.x, -w.y);
+  };
+  for (int fl = warp; fl < FPB; fl += kWarps) {
+    if (f0 + fl >= F) break;                    // warp-uniform
+    float2 v[2][8];
+    // ---- pass 1 (Ns = 1): window, pack z[n] = x[2n] + i x[2n+1], butterfly, no twiddles
     {
       const float2* sp = reinterpret_cast<const float2*>(samp + fl * HOP);   // fl*HOP is even -> 8-byte aligned
-      const float2* hp2 = reinterpret_cast<const float2*>(hann);
+      const float2* hp = reinterpret_cast<const float2*>(hann);
 #pragma unroll
-      for (int n = lt; n < HALF; n += 64) {
-        const float2 x = sp[n], w = hp2[n];
-        d0[n] = make_float2(x.x * w.x, x.y * w.y);
-      }
-    }
-    // 512-point Stockham FFT: four radix-4 passes (Ns = 1, 4, 16, 64; 128 butterflies each, 2 per thread) and one radix-2
-    // pass (Ns = 256).  Only the 64 threads of this frame group synchronise (named barrier 1+grp), not the whole CTA.
-    auto group_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory"); };
-    auto cmul = [](float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); };
-    group_sync();
-#pragma unroll 1
-    for (int s4 = 0; s4 < 4; ++s4) {
-      const int Ns = 1 << (2 * s4);
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {
-        const int jdx = lt + qq * 64;                 // 0..127
-        const int k = jdx & (Ns - 1);
-        // twiddles exp(-2*pi*i*r*k/(4*Ns)) = W_1024^(r*k*256/Ns), r = 1..3 (index < 768: fold with W^(512+m) = -W^m)
-        const int tstep = k * (256 / Ns);
-        float2 v0 = d0[jdx], v1 = d0[jdx + 128], v2 = d0[jdx + 256], v3 = d0[jdx + 384];
-        const float2 w1 = tw[tstep], w2 = tw[2 * tstep];
-        const int t3 = 3 * tstep;
-        const float2 w3 = t3 < HALF ? tw[t3] : make_float2(-tw[t3 - HALF].x, -tw[t3 - HALF].y);
-        v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
-        // radix-4 butterfly (forward transform: -i rotation)
-        const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y), a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-        const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y), a3 = make_float2(v1.x - v3.x, v1.y - v3.y);
-        const int dst = ((jdx - k) << 2) + k;
-        d1[dst] = make_float2(a0.x + a2.x, a0.y + a2.y);
-        d1[dst + Ns] = make_float2(a1.x + a3.y, a1.y - a3.x);
-        d1[dst + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-        d1[dst + 3 * Ns] = make_float2(a1.x - a3.y, a1.y + a3.x);
-      }
-      group_sync();
-      float2* tmp = d0; d0 = d1; d1 = tmp;
-    }
-    {
-      const int Ns = 256;
+        for (int r = 0; r < 8; ++r) {
+          const int n = lane + 32 * u + 64 * r;
+          const float2 x = sp[n], w = hp[n];
+          v[u][r] = make_float2(x.x * w.x, x.y * w.y);
+        }
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int jdx = lt + qq * 64;                 // 0..255
-        const int k = jdx & (Ns - 1);
-        const float2 w = tw[k * (HALF / Ns)];
-        const float2 a = d0[jdx], bw = cmul(d0[jdx + 256], w);
-        const int dst = ((jdx - k) << 1) + k;
-        d1[dst] = make_float2(a.x + bw.x, a.y + bw.y);
-        d1[dst + Ns] = make_float2(a.x - bw.x, a.y - bw.y);
+      for (int u = 0; u < 2; ++u) {
+        dft8(v[u]);
+        const int j0 = (lane + 32 * u) * 8;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) wb[slot(j0 + r)] = v[u][r];
       }
-      group_sync();
-      float2* tmp = d0; d0 = d1; d1 = tmp;
+      __syncwarp();
     }
-    // split post-pass: X[k] = E + W^k * O.  Bins k and 512-k share Z[k], Z[512-k] and the twiddle
-    // (E(512-k) = conj E(k), O(512-k) = conj O(k), W^(512-k) = -conj W^k), so each thread produces two magnitudes.
-    for (int k = lt; k <= HALF / 2; k += 64) {
-      const float2 zk = d0[k & (HALF - 1)];
-      const float2 zr = d0[(HALF - k) & (HALF - 1)];
+    // ---- passes 2, 3 (Ns = 8, 64): twiddle exp(-2*pi*i*r*k/(8*Ns)) = W_1024^(r*k*128/Ns)
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int Ns = pass == 0 ? 8 : 64;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[u][r] = wb[slot(j + 64 * r)];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        const int k = j & (Ns - 1);
+        const int tstep = k * (128 / Ns);
+#pragma unroll
+        for (int r = 1; r < 8; ++r) v[u][r] = cmul(v[u][r], twd(r * tstep));
+        dft8(v[u]);
+        const int j0 = ((j - k) << 3) + k;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) wb[slot(j0 + r * Ns)] = v[u][r];
+      }
+      __syncwarp();
+    }
+    // ---- split post-pass: X[k] = E + W^k * O.  Bins k and 512-k share Z[k], Z[512-k] and the twiddle
+    // (E(512-k) = conj E(k), O(512-k) = conj O(k), W^(512-k) = -conj W^k), so each step yields two magnitudes.
+    float esum = 0.f;
+    for (int k = lane; k <= HALF / 2; k += 32) {
+      const float2 zk = wb[slot(k & (HALF - 1))];
+      const float2 zr = wb[slot((HALF - k) & (HALF - 1))];
       const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
       const float2 o = make_float2(0.5f * (zk.y + zr.y), -0.5f * (zk.x - zr.x));        // -i/2 * (zk - conj(zr))
-      const float2 w = tw[k];
-      const float2 wo = make_float2(o.x * w.x - o.y * w.y, o.x * w.y + o.y * w.x);
+      const float2 wo = cmul(o, tw[k]);
       const float xr = e.x + wo.x, xi = e.y + wo.y;                                      // X[k]
       const float yr = e.x - wo.x, yi = -e.y + wo.y;                                     // X[512-k] = conj(E) - conj(W^k O)
-      mag[fl][k] = sqrtf(xr * xr + xi * xi);
-      mag[fl][HALF - k] = sqrtf(yr * yr + yi * yi);
+      const float p0 = xr * xr + xi * xi, p1 = yr * yr + yi * yi;
+      mg[k] = sqrtf(p0);
+      mg[HALF - k] = sqrtf(p1);
+      esum += k == HALF / 2 ? p0 : p0 + p1;     // bin 256 is its own mirror
     }
-    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");   // the group's buffers are reused by its next frame
+    esum = warp_sum(esum);                      // energy: L2 norm over the 513 bins (stft.py:158)
+    if (lane == 0) s_en[fl] = sqrtf(esum);
+    __syncwarp();
+    // ---- mel projection + log compression (stft.py:156-157) over the non-zero band of each filter row
+    for (int m = lane; m < n_mels; m += 32) {
+      const int lo = band[2 * m], hi = band[2 * m + 1];
+      const float* br = basis + static_cast<long long>(m) * NBINS;
+      float acc = 0.f;
+      for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(br + k), mg[k], acc);
+      s_mel[m * MELLD + fl] = logf(fmaxf(acc, 1e-5f));
+    }
+    __syncwarp();                               // mg / wb are reused by this warp's next frame
   }
   __syncthreads();
-
-  // energy: L2 norm over the 513 bins (stft.py:158); warp per frame
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < FPB && f0 + warp < F) {
-    float s = 0.f;
-    for (int k = lane; k < NBINS; k += 32) s += mag[warp][k] * mag[warp][k];
-    s = warp_sum(s);
-    if (lane == 0) energy[static_cast<long long>(b) * F + f0 + warp] = sqrtf(s);
-  }
-  // mel projection + log compression (stft.py:156-157)
-  for (int i = threadIdx.x; i < n_mels * FPB; i += 256) {
+  // coalesced stores: FPB consecutive frames of one mel row are contiguous in mel[b][m][:]
+  const int nf = min(FPB, F - f0);
+  for (int i = threadIdx.x; i < n_mels * FPB; i += kWarps * 32) {
     const int m = i / FPB, fl = i % FPB;
-    if (f0 + fl >= F) continue;
-    const int lo = band[2 * m], hi = band[2 * m + 1];
-    const float* br = basis + static_cast<long long>(m) * NBINS;
-    float acc = 0.f;
-    for (int k = lo; k < hi; ++k) acc = fmaf(br[k], mag[fl][k], acc);
-    mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = logf(fmaxf(acc, 1e-5f));
+    if (fl < nf) mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = s_mel[m * MELLD + fl];
   }
+  if (threadIdx.x < nf) energy[static_cast<long long>(b) * F + f0 + threadIdx.x] = s_en[threadIdx.x];
 }
 
 }  // namespace
@@ -177,14 +210,15 @@ extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const f
   mel_band_kernel<<<ceil_div(n_mels, 8), 256, 0, s>>>(mel_basis, n_mels, band_ws);
   SB_LAUNCH_OK();
   dim3 grid(ceil_div(F, FPB), B);
-  constexpr size_t smem = sizeof(float2) * 4 * 2 * HALF + sizeof(float2) * HALF + sizeof(float) * FPB * (NBINS + 3) +
-                          sizeof(float) * NSAMP + sizeof(float) * NFFT;
+  const size_t smem = sizeof(float2) * HALF + sizeof(float2) * kWarps * WBUF + sizeof(float) * NFFT + sizeof(float) * NSAMP +
+                      sizeof(float) * kWarps * MAGLD + sizeof(float) * FPB + sizeof(float) * n_mels * MELLD;
+  SB_REQUIRE(smem <= 113 * 1024, "stft_mel: n_mels=%d needs %zu bytes of shared memory", n_mels, smem);
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA_OK(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SB_CUDA_OK(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr_set = true;
   }
-  stft_mel_kernel<<<grid, 256, smem, s>>>(y, N, F, mel_basis, band_ws, n_mels, mel, energy);
+  stft_mel_kernel<<<grid, kWarps * 32, smem, s>>>(y, N, F, mel_basis, band_ws, n_mels, mel, energy);
   SB_LAUNCH_OK();
   return 0;
 }

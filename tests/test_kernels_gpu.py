@@ -160,6 +160,40 @@ def test_attention(cuda, dtype, impl, T, v_layout):
     assert rel_err(got, ref) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+def test_attention_tc_edge_lengths_and_rising_max(cuda, dtype):
+    """Key-padding edge cases of the tensor-core kernel (a key half of a tile with no valid key, one valid key,
+    exact tile boundaries) and scores whose row maximum keeps growing from key tile to key tile, so the lazily
+    raised running max / in-TMEM rescale of the accumulator is exercised (Modules.py:16-23 semantics)."""
+    ops = _ops()
+    H, T = 4, 400
+    lens = torch.tensor([1, 40, 64, 65, 128, 129, 200, 400], dtype=torch.int64)
+    B = lens.numel()
+    g = torch.Generator().manual_seed(11)
+    qk = torch.randn(B, T, 512, generator=g)
+    qk[..., 256:] *= torch.linspace(0.1, 1.6, T).view(1, T, 1)          # keys grow with position -> maxima keep rising
+    v = torch.randn(B, T, 256, generator=g)
+    qkq, vq = qk.to(dtype).float(), v.to(dtype).float()
+    q = qkq[..., :256].view(B, T, H, 64).permute(0, 2, 1, 3)
+    k = qkq[..., 256:].view(B, T, H, 64).permute(0, 2, 1, 3)
+    vv = vq.view(B, T, H, 64).permute(0, 2, 1, 3)
+    s = (q @ k.transpose(-1, -2)).masked_fill(so.mask_from_lengths(lens, T)[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vv).permute(0, 2, 1, 3).reshape(B, T, 256)
+    if dtype == torch.bfloat16:
+        got = ops.attention(torch.cat([qk, v], dim=-1).to(cuda, dtype), None, lens.to(cuda), H, impl=ops.IMPL_TC)
+    else:
+        Tp = (T + 63) // 64 * 64
+        vt = torch.zeros(B, 256, Tp, dtype=dtype)
+        vt[:, :, :T] = v.transpose(1, 2)
+        got = ops.attention(qk.to(cuda, dtype), vt.to(cuda), lens.to(cuda), H, impl=ops.IMPL_TC)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    # f32 runs as tf32 on the tensor pipe: operand rounding (2^-11) times scores of magnitude ~40 -> percent-level p error
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 2e-2
+    for b in range(B):
+        assert rel_err(got[b], ref[b]) < tol, (b, int(lens[b]))
+
+
 def test_embed_add_cast(cuda):
     ops = _ops()
     g = torch.Generator().manual_seed(3)

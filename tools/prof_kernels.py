@@ -71,6 +71,11 @@ def main():
     ctx = torch.empty(B, T, 256, device=dev, dtype=dt)
     cases["attention"] = (lambda: ops.attention(qk, vt, lens, 4, out=ctx, impl=ops.IMPL_TC),
                           4.0 * B * 4 * T * T * 64, B * T * 1024 * es, "tensor")
+    if dt == torch.bfloat16:   # the layout the engine uses in bf16: fused [B,T,768] buffer, V read row-major
+        qkv = torch.empty(B, T, 768, device=dev, dtype=dt)
+        ops.conv1d(x256, wqkv, bqkv, out=qkv, impl=ops.IMPL_TC)
+        cases["attention_qkv"] = (lambda: ops.attention(qkv, None, lens, 4, out=ctx, impl=ops.IMPL_TC),
+                                  4.0 * B * 4 * T * T * 64, B * T * 1024 * es, "tensor")
     mel80 = rnd(B, T, 80)
     wp0, bp0 = rnd(5, 512, 80, scale=0.05), fp(512)
     h512 = torch.empty(B, T, 512, device=dev, dtype=dt)
@@ -101,7 +106,7 @@ def main():
 
     rows = []
     for name, (fn, flops, nbytes, bound) in cases.items():
-        if args.only and name != args.only:
+        if args.only and name not in args.only.split(","):
             continue
         for _ in range(2):
             fn()
