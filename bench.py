@@ -55,7 +55,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
+
+    def mark(self):
+        """Samples before this call (nvidia-smi start-up, warm-up) are not part of the timed region."""
+        self.first = len(self.rows)
 
     def __enter__(self):
         try:
@@ -81,14 +85,15 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] if len(self.rows) > self.first else self.rows
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         reasons = []
         for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), start=3):
-            if any(len(r) > i and r[i].lower().startswith("active") for r in self.rows):
+            if any(len(r) > i and r[i].lower().startswith("active") for r in rows):
                 reasons.append(name)
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -238,6 +243,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    enqueue = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -246,6 +253,7 @@ def main():
         for i in range(steps):
             fn(i)
         e1.record()
+        enqueue[0] = time.perf_counter() - t0        # host time to enqueue all steps (launch-bound if ~ the device time)
         barrier()
         wall = time.perf_counter() - t0
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -253,9 +261,15 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / 1e3, wall
 
+    # nvidia-smi starts (and takes its driver locks) during the warm-up, not inside the timed region
+    clocks = ClockSampler(local)
+    clocks.__enter__()
     for i in range(args.warmup):
         step(resident[i % NBUF])
     torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    while not clocks.rows and clocks.proc is not None and time.perf_counter() - t_w < 3.0:
+        time.sleep(0.05)                              # first sample seen: the sampler is up
     if args.graph:
         from styler_b200 import GraphedSTYLER
         g0 = GraphedSTYLER(model, (resident[0]["src_seq"], resident[0]["mel_target"], resident[0]["mel_aug"], resident[0]["p_norm"],
@@ -269,8 +283,9 @@ def main():
     eng = model._engine_for()
     eng.prof = []
     launches0 = _lib.launch_count()
-    with ClockSampler(local) as clocks:
-        secs, wall = timed(lambda i: step(resident[i % NBUF]), args.steps)
+    clocks.mark()
+    secs, wall = timed(lambda i: step(resident[i % NBUF]), args.steps)
+    clocks.__exit__()
     launches = _lib.launch_count() - launches0
     prof, eng.prof = eng.prof, None
     torch.cuda.synchronize()
@@ -357,7 +372,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_secs / args.steps},
         "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
-        "wall_s_timed_region": wall}))
+        "wall_s_timed_region": wall, "host_enqueue_ms_per_step": 1e3 * enqueue[0] / args.steps}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

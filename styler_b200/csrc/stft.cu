@@ -19,6 +19,8 @@ constexpr int NSAMP = (FPB - 1) * HOP + NFFT;
 constexpr int WBUF = HALF + HALF / 16;               // complex work buffer per warp, skewed: slot(i) = i + (i >> 4)
 constexpr int MAGLD = NBINS + 3;
 constexpr int MELLD = FPB + 1;
+constexpr int kBasisCap = 1536;                      // floats of smem for the non-zero bands of the mel basis (727 used by the
+                                                     // reference's 80-mel Slaney basis); larger bases are read from global
 
 __global__ void mel_band_kernel(const float* __restrict__ basis, int n_mels, int32_t* __restrict__ band) {
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -68,12 +70,17 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
                                                                   float* __restrict__ mel, float* __restrict__ energy) {
   extern __shared__ __align__(16) uint8_t stft_smem[];
   float2* tw = reinterpret_cast<float2*>(stft_smem);                       // W_1024^k, k < 512
-  float2* wbuf = tw + HALF;                                                // [kWarps][WBUF]
-  float* hann = reinterpret_cast<float*>(wbuf + kWarps * WBUF);            // [NFFT] periodic Hann
-  float* samp = hann + NFFT;                                               // [NSAMP]
+  float2* twA = tw + HALF;                                                 // W_64^k,  k < 8   (pass-2 base twiddles)
+  float2* twB = twA + 8;                                                   // W_512^k, k < 64  (pass-3 base twiddles)
+  float2* wbuf = twB + 64;                                                 // [kWarps][WBUF]
+  float* samp = reinterpret_cast<float*>(wbuf + kWarps * WBUF);            // [NSAMP]
   float* mag = samp + NSAMP;                                               // [kWarps][MAGLD]
   float* s_en = mag + kWarps * MAGLD;                                      // [FPB]
-  float* s_mel = s_en + FPB;                                               // [n_mels][MELLD]
+  float* s_basis = s_en + FPB;                                             // [kBasisCap] bands of the mel basis, back to back
+  int* s_lo = reinterpret_cast<int*>(s_basis + kBasisCap);                 // [n_mels] first bin of the band
+  int* s_hi = s_lo + n_mels;                                               // [n_mels] one past the last bin
+  int* s_off = s_hi + n_mels;                                              // [n_mels + 1] offset of the band in s_basis
+  float* s_mel = reinterpret_cast<float*>(s_off + n_mels + 1);             // [n_mels][MELLD]
   const int b = blockIdx.y, f0 = blockIdx.x * FPB;
   const float* yb = y + static_cast<long long>(b) * N;
   for (int i0 = 0; i0 < NSAMP; i0 += 4 * kWarps * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
@@ -96,8 +103,27 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
     float sn, cs;
     sincospif(-static_cast<float>(k) / 512.0f, &sn, &cs);
     tw[k] = make_float2(cs, sn);
-    hann[k] = 0.5f - 0.5f * cs;                 // cos(2*pi*k/1024) = Re W^k ;  cos(2*pi*(k+512)/1024) = -Re W^k
-    hann[k + HALF] = 0.5f + 0.5f * cs;
+  }
+  if (threadIdx.x < 72) {
+    const int k = threadIdx.x < 8 ? threadIdx.x : threadIdx.x - 8;
+    float sn, cs;
+    sincospif(-static_cast<float>(k) / (threadIdx.x < 8 ? 32.0f : 256.0f), &sn, &cs);
+    (threadIdx.x < 8 ? twA : twB)[k] = make_float2(cs, sn);
+  }
+  for (int m = threadIdx.x; m < n_mels; m += kWarps * 32) { s_lo[m] = band[2 * m]; s_hi[m] = band[2 * m + 1]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int m = 0; m < n_mels; ++m) { s_off[m] = off; off += s_hi[m] - s_lo[m]; }
+    s_off[n_mels] = off;
+  }
+  __syncthreads();
+  const bool basis_in_smem = s_off[n_mels] <= kBasisCap;
+  if (basis_in_smem) {
+    for (int m = threadIdx.x >> 5; m < n_mels; m += kWarps) {
+      const int lo = s_lo[m], w = s_hi[m] - lo;
+      for (int i = threadIdx.x & 31; i < w; i += 32) s_basis[s_off[m] + i] = basis[static_cast<long long>(m) * NBINS + lo + i];
+    }
   }
   __syncthreads();
 
@@ -105,24 +131,23 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   float2* wb = wbuf + warp * WBUF;
   float* mg = mag + warp * MAGLD;
   auto slot = [](int i) { return i + (i >> 4); };
-  auto twd = [&](int m) {                       // W_1024^m for m < 1024
-    const float2 w = tw[m & (HALF - 1)];
-    return m < HALF ? w : make_float2(-w.x, -w.y);
-  };
   for (int fl = warp; fl < FPB; fl += kWarps) {
     if (f0 + fl >= F) break;                    // warp-uniform
     float2 v[2][8];
     // ---- pass 1 (Ns = 1): window, pack z[n] = x[2n] + i x[2n+1], butterfly, no twiddles
     {
       const float2* sp = reinterpret_cast<const float2*>(samp + fl * HOP);   // fl*HOP is even -> 8-byte aligned
-      const float2* hp = reinterpret_cast<const float2*>(hann);
+      const float4* tw2 = reinterpret_cast<const float4*>(tw);               // (Re W^2n, Im W^2n, Re W^(2n+1), Im W^(2n+1))
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int n = lane + 32 * u + 64 * r;
-          const float2 x = sp[n], w = hp[n];
-          v[u][r] = make_float2(x.x * w.x, x.y * w.y);
+          const float2 x = sp[n];
+          // periodic Hann: 0.5 - 0.5 cos(2 pi i / 1024), cos(2 pi i / 1024) = Re W^i = -Re W^(i-512)
+          const float4 c = tw2[n & (HALF / 2 - 1)];
+          const float sg = n < HALF / 2 ? -0.5f : 0.5f;
+          v[u][r] = make_float2(x.x * fmaf(sg, c.x, 0.5f), x.y * fmaf(sg, c.z, 0.5f));
         }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -148,9 +173,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
       for (int u = 0; u < 2; ++u) {
         const int j = lane + 32 * u;
         const int k = j & (Ns - 1);
-        const int tstep = k * (128 / Ns);
-#pragma unroll
-        for (int r = 1; r < 8; ++r) v[u][r] = cmul(v[u][r], twd(r * tstep));
+        // twiddles w^r, w = exp(-2*pi*i*k/(8*Ns)), r = 1..7: one conflict-free table read + a product tree
+        const float2 w1 = pass == 0 ? twA[k] : twB[k];
+        const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+        v[u][1] = cmul(v[u][1], w1); v[u][2] = cmul(v[u][2], w2); v[u][3] = cmul(v[u][3], w3); v[u][4] = cmul(v[u][4], w4);
+        v[u][5] = cmul(v[u][5], cmul(w4, w1)); v[u][6] = cmul(v[u][6], cmul(w3, w3)); v[u][7] = cmul(v[u][7], cmul(w4, w3));
         dft8(v[u]);
         const int j0 = ((j - k) << 3) + k;
 #pragma unroll
@@ -179,10 +206,15 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
     __syncwarp();
     // ---- mel projection + log compression (stft.py:156-157) over the non-zero band of each filter row
     for (int m = lane; m < n_mels; m += 32) {
-      const int lo = band[2 * m], hi = band[2 * m + 1];
-      const float* br = basis + static_cast<long long>(m) * NBINS;
+      const int lo = s_lo[m], hi = s_hi[m];
       float acc = 0.f;
-      for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(br + k), mg[k], acc);
+      if (basis_in_smem) {
+        const float* br = s_basis + s_off[m] - lo;
+        for (int k = lo; k < hi; ++k) acc = fmaf(br[k], mg[k], acc);
+      } else {
+        const float* br = basis + static_cast<long long>(m) * NBINS;
+        for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(br + k), mg[k], acc);
+      }
       s_mel[m * MELLD + fl] = logf(fmaxf(acc, 1e-5f));
     }
     __syncwarp();                               // mg / wb are reused by this warp's next frame
@@ -210,8 +242,9 @@ extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const f
   mel_band_kernel<<<ceil_div(n_mels, 8), 256, 0, s>>>(mel_basis, n_mels, band_ws);
   SB_LAUNCH_OK();
   dim3 grid(ceil_div(F, FPB), B);
-  const size_t smem = sizeof(float2) * HALF + sizeof(float2) * kWarps * WBUF + sizeof(float) * NFFT + sizeof(float) * NSAMP +
-                      sizeof(float) * kWarps * MAGLD + sizeof(float) * FPB + sizeof(float) * n_mels * MELLD;
+  const size_t smem = sizeof(float2) * (HALF + 8 + 64) + sizeof(float2) * kWarps * WBUF + sizeof(float) * NSAMP +
+                      sizeof(float) * kWarps * MAGLD + sizeof(float) * FPB + sizeof(float) * kBasisCap +
+                      sizeof(int) * (3 * n_mels + 1) + sizeof(float) * n_mels * MELLD;
   SB_REQUIRE(smem <= 113 * 1024, "stft_mel: n_mels=%d needs %zu bytes of shared memory", n_mels, smem);
   static bool attr_set = false;
   if (!attr_set) {

@@ -76,6 +76,10 @@ def main():
         ops.conv1d(x256, wqkv, bqkv, out=qkv, impl=ops.IMPL_TC)
         cases["attention_qkv"] = (lambda: ops.attention(qkv, None, lens, 4, out=ctx, impl=ops.IMPL_TC),
                                   4.0 * B * 4 * T * T * 64, B * T * 1024 * es, "tensor")
+        # random-init-like score statistics (std ~0.4, as in the bench model): the running max is raised on the first key tile only
+        qkv_lo = torch.cat([rnd(B, T, 256, scale=0.075), rnd(B, T, 256, scale=0.6), rnd(B, T, 256)], dim=-1).contiguous()
+        cases["attention_lowvar"] = (lambda: ops.attention(qkv_lo, None, lens, 4, out=ctx, impl=ops.IMPL_TC),
+                                     4.0 * B * 4 * T * T * 64, B * T * 1024 * es, "tensor")
     mel80 = rnd(B, T, 80)
     wp0, bp0 = rnd(5, 512, 80, scale=0.05), fp(512)
     h512 = torch.empty(B, T, 512, device=dev, dtype=dt)
