@@ -73,14 +73,20 @@ __device__ __forceinline__ void store16(T* p, const float (&v)[16]) {
 // generic runtime-switched body was ~1850 SASS instructions per 32 columns (tanhf inlined 64x) and ran at ~7 clk/instr.
 // FAST: output staged through smem + TMA store, residual (if any) staged through smem, no V^T / fp32 copy / row dot:
 // the common case, compiled without the alternative paths (instruction issue, not memory, bounds this epilogue).
-template <typename T, int ACT, bool LN, bool FAST>
+// PERSIST (small-K GEMMs, FAST epilogue only): the CTA loops over output tiles (tile = blockIdx.x + i * gridDim.x) with
+// TWO accumulators in TMEM, a dedicated output/residual staging buffer next to the operand ring, and the operand ring
+// running on across tile boundaries.  The loads and MMAs of tile i+1 then overlap the epilogue and the TMA store of tile
+// i inside one CTA: with K <= 1024 a tile's mainloop (2-8 k cycles of MMA) is shorter than its TMA round trip plus its
+// epilogue (~6 k cycles), which the one-tile-per-CTA form pays serially (phase stamps: profiles/phase_timing_r1c.txt).
+template <typename T, int ACT, bool LN, bool FAST, bool PERSIST>
 __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmOut,
                                                              const __grid_constant__ CUtensorMap tmRes,
                                                              const EpiParams ep, int Tlen, int n_tiles,
                                                              int tiles_per_utt, int KS, int pad, int kb_per_tap,
-                                                             int BN, int stages) {
+                                                             int BN, int stages, int total_tiles) {
+  static_assert(!PERSIST || FAST, "the persistent tile loop only exists for the staged (FAST) epilogue");
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int kBKE = 128 / sizeof(T);  // elements per 128-byte k-slice
 
@@ -88,32 +94,32 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_stage_bytes = BN * 128;
   const int stage_bytes = kAStageBytes + b_stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  const int n_box = (BN * static_cast<int>(sizeof(T))) / 128;     // 16 KB [128 rows x 128 B] boxes per output tile
+  // epilogue staging (output rows / residual rows): its own region when persistent, the idle operand ring otherwise
+  uint8_t* stg = PERSIST ? smem + stages * stage_bytes : smem;
+  uint8_t* tail = smem + stages * stage_bytes + (PERSIST ? n_box * kAStageBytes : 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + stages;
-  uint64_t* tmem_full = empty + stages;
-  uint64_t* res_full = tmem_full + 1;
+  uint64_t* tmem_full = empty + stages;        // [2] MMA -> epilogue, one per accumulator
+  uint64_t* tmem_empty = tmem_full + 2;        // [2] epilogue -> MMA (persistent only)
+  uint64_t* res_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
-  float* s_par = reinterpret_cast<float*>(smem + stages * stage_bytes + 256);   // [4][256]: bias, gamma, beta, dot_w
+  float* s_par = reinterpret_cast<float*>(tail + 256);                          // [4][256]: bias, gamma, beta, dot_w
   float* s_x = s_par + 1024;                                                    // [256 threads][4]: LN / dot exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = ep.dbg != nullptr ? ep.dbg + static_cast<long long>(blockIdx.x) * 8 : nullptr;
   if (dbg != nullptr && threadIdx.x == 0) dbg[0] = clock64();
-  const int nt = blockIdx.x % n_tiles, mt = blockIdx.x / n_tiles;
-  const int b = mt / tiles_per_utt, t0 = (mt % tiles_per_utt) * kBM;
-  const int n0 = nt * BN;
   const int num_kb = KS * kb_per_tap;
-  const uint32_t tmem_cols = tmem_cols_pow2(BN);
-  const bool tile_to_vt = !FAST && ep.vt != nullptr && n0 >= ep.vt_col0;
-  const bool st_out = FAST || (ep.stage_out != 0 && !tile_to_vt);            // TMA-store this tile's output from smem
-  const bool st_res = FAST ? ep.residual != nullptr : ep.stage_res != 0;      // TMA-load this tile's residual into smem
-  const int n_box = (BN * static_cast<int>(sizeof(T))) / 128;     // 16 KB [128 rows x 128 B] boxes per tile
+  const uint32_t acc_cols = tmem_cols_pow2(BN);                      // columns of one accumulator
+  const uint32_t tmem_cols = PERSIST ? 2 * acc_cols : acc_cols;
+  const int tile_step = PERSIST ? static_cast<int>(gridDim.x) : total_tiles;   // non-persistent: exactly one tile per CTA
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 1); }
     mbar_init(res_full, 1);
     fence_mbar_init();
   }
@@ -129,44 +135,59 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], stage_bytes);
-        const int tap = kb / kb_per_tap, kc = (kb % kb_per_tap) * kBKE;
-        uint8_t* sa = smem + s * stage_bytes;
-        tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap - pad, b);
-        tma_load_3d(sa + kAStageBytes, &tmB, &full[s], kc, n0, tap);
-      }
-      if (st_res) {   // all MMAs done -> the pipeline stages are free: stage the residual tile there
-        mbar_wait(tmem_full, 0);
-        mbar_arrive_expect_tx(res_full, n_box * kAStageBytes);
-        for (int bx = 0; bx < n_box; ++bx)
-          tma_load_3d(smem + bx * kAStageBytes, &tmRes, res_full, n0 + bx * kBKE, t0, b);
+      int g = 0;                                   // k-block counter over all tiles of this CTA: the ring never drains
+      for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step) {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        const int b = mt / tiles_per_utt, t0 = (mt % tiles_per_utt) * kBM, n0 = nt * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % stages;
+          const uint32_t ph = (g / stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], stage_bytes);
+          const int tap = kb / kb_per_tap, kc = (kb % kb_per_tap) * kBKE;
+          uint8_t* sa = smem + s * stage_bytes;
+          tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap - pad, b);
+          tma_load_3d(sa + kAStageBytes, &tmB, &full[s], kc, n0, tap);
+        }
+        if (!PERSIST && (FAST ? ep.residual != nullptr : ep.stage_res != 0)) {
+          // all MMAs done -> the pipeline stages are free: stage the residual tile there
+          mbar_wait(&tmem_full[0], 0);
+          mbar_arrive_expect_tx(res_full, n_box * kAStageBytes);
+          for (int bx = 0; bx < n_box; ++bx)
+            tma_load_3d(stg + bx * kAStageBytes, &tmRes, res_full, n0 + bx * kBKE, t0, b);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, kBM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&full[s], ph);
-        if (dbg != nullptr && kb == 0) dbg[2] = clock64();
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_addr = a_addr + kAStageBytes;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte slice
-          umma_ss<kTf32>(tmem_base, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step, ++it) {
+        const int ab = PERSIST ? (it & 1) : 0;
+        const uint32_t acc = tmem_base + ab * acc_cols;
+        if (PERSIST) {                             // the epilogue has drained this accumulator (tile it-2)
+          mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
         }
-        umma_commit(&empty[s]);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % stages;
+          const uint32_t ph = (g / stages) & 1;
+          mbar_wait(&full[s], ph);
+          if (dbg != nullptr && kb == 0) dbg[2] = clock64();
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + kAStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte slice
+            umma_ss<kTf32>(acc, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[ab]);
+        if (dbg != nullptr) dbg[3] = clock64();
       }
-      umma_commit(tmem_full);
-      if (dbg != nullptr) dbg[3] = clock64();
     }
     __syncwarp();
   } else {
@@ -179,9 +200,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     const bool split = (BN % 32) == 0;
     const int c_begin = split ? hf * (BN / 2) : (hf == 0 ? 0 : BN);
     const int c_end = split ? c_begin + BN / 2 : BN;
+    int it = 0;
+    if (PERSIST && ep.residual != nullptr && threadIdx.x == 64 && static_cast<int>(blockIdx.x) < total_tiles) {
+      // residual rows of this CTA's first tile -> staging buffer (later tiles: issued when the previous store has drained)
+      const int nt = blockIdx.x % n_tiles, mt = blockIdx.x / n_tiles;
+      mbar_arrive_expect_tx(res_full, n_box * kAStageBytes);
+      for (int bx = 0; bx < n_box; ++bx)
+        tma_load_3d(stg + bx * kAStageBytes, &tmRes, res_full, nt * BN + bx * kBKE, (mt % tiles_per_utt) * kBM, mt / tiles_per_utt);
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step, ++it) {
+    const int nt = tile % n_tiles, mt = tile / n_tiles;
+    const int b = mt / tiles_per_utt, t0 = (mt % tiles_per_utt) * kBM;
+    const int n0 = nt * BN;
+    const int ab = PERSIST ? (it & 1) : 0;
+    const bool tile_to_vt = !FAST && ep.vt != nullptr && n0 >= ep.vt_col0;
+    const bool st_out = FAST || (ep.stage_out != 0 && !tile_to_vt);            // TMA-store this tile's output from smem
+    const bool st_res = FAST ? ep.residual != nullptr : ep.stage_res != 0;      // this tile's residual arrives in smem by TMA
     const int t = t0 + r;
     const bool row_ok = t < Tlen;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t taddr = tmem_base + ab * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
     const bool masked = ep.lens != nullptr && row_ok && t >= static_cast<int>(ep.lens[b]);
     constexpr bool has_ln = LN;
     const bool has_res = ep.residual != nullptr;
@@ -205,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
 
     // Per-column parameters of this N tile staged in smem once per CTA (while the mainloop runs): reading them with
     // 16 dependent global loads per chunk was the dominant epilogue cost.
-    {
+    if (it == 0 || n_tiles > 1) {   // (persistent: every reader of the previous tile's values has passed the pre-store barrier)
       const int te = threadIdx.x - 64;
       for (int i = te; i < BN; i += 256) {
         s_par[i] = ep.bias != nullptr ? ep.bias[n0 + i] : 0.f;
@@ -228,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     };
 
     // smem staging address of columns c..c+15 of this thread's row: box (c*es/128), 128-byte row r, 16-byte chunks XOR (r&7)
-    uint8_t* stage_row = smem + r * 128;
+    uint8_t* stage_row = stg + r * 128;
     const int sw = r & 7;
     auto stage_ptr = [&](int c, int chunk) -> uint8_t* {
       const int byte0 = c * static_cast<int>(sizeof(T));
@@ -297,9 +334,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       }
     };
 
-    mbar_wait(tmem_full, 0);
+    mbar_wait(&tmem_full[ab], PERSIST ? ((it >> 1) & 1) : 0);
     tc_fence_after();
-    if (st_res) mbar_wait(res_full, 0);
+    if (st_res) mbar_wait(res_full, PERSIST ? (it & 1) : 0);
+    else if (PERSIST && it > 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // thread 64 has seen the previous store drain
     if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
 
     float mean = 0.f, rstd = 1.f;
@@ -454,14 +492,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     if (dbg != nullptr) t_pre_store = clock64();
     if (st_out) {   // smem tile -> global with TMA (rows >= T are clipped by the tensor map)
       fence_proxy_async_smem();
+      if (PERSIST) tc_fence_before();              // this tile's TMEM reads are ordered before the hand-back below
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 64) {
-        for (int bx = 0; bx < n_box; ++bx) tma_store_3d(&tmOut, smem + bx * kAStageBytes, n0 + bx * kBKE, t0, b);
+        if (PERSIST) mbar_arrive(&tmem_empty[ab]); // the MMA thread may overwrite this accumulator (tile it+2)
+        for (int bx = 0; bx < n_box; ++bx) tma_store_3d(&tmOut, stg + bx * kAStageBytes, n0 + bx * kBKE, t0, b);
         tma_store_commit();
         tma_store_wait_read();
+        const int nx = tile + tile_step;
+        if (PERSIST && st_res && nx < total_tiles) {   // staging is free again: fetch the next tile's residual rows
+          const int nnt = nx % n_tiles, nmt = nx / n_tiles;
+          mbar_arrive_expect_tx(res_full, n_box * kAStageBytes);
+          for (int bx = 0; bx < n_box; ++bx)
+            tma_load_3d(stg + bx * kAStageBytes, &tmRes, res_full, nnt * BN + bx * kBKE, (nmt % tiles_per_utt) * kBM,
+                        nmt / tiles_per_utt);
+        }
       }
     }
     if (dbg != nullptr && threadIdx.x == 64) { dbg[6] = clock64(); if (!has_ln) dbg[3] = t_pre_store; }
+    }   // tile loop
   }
 
   tc_fence_before();
@@ -479,6 +528,25 @@ int smem_budget_bytes() {
     if (v > 220 * 1024) v = 220 * 1024;
   }
   return v;
+}
+
+// STYLER_TC_PERSIST: 0 = one tile per CTA everywhere, 1 (default) = persistent form where two CTAs per SM still fit
+// (two accumulators of <= 128 TMEM columns), 2 = also the one-CTA-per-SM form (N = 256 LayerNorm rows; measured slower:
+// out-proj 0.037 -> 0.045 ms, its epilogue is issue-bound and loses the second CTA's warps).
+int persist_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("STYLER_TC_PERSIST"); v = e != nullptr ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
+  return v;
+}
+
+int num_sms() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
 }
 
 int pick_bn(const styler_conv1d_args& a, int m_tiles) {
@@ -517,17 +585,34 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   constexpr int bke = 128 / es;
   const int tiles_per_utt = ceil_div(a.T, kBM);
   const int m_tiles = a.B * tiles_per_utt;
-  const int BN = pick_bn(a, m_tiles);
-  SB_REQUIRE(BN > 0, "conv1d_tc: no valid N tile for N=%d", a.N);
-  const int n_tiles = a.N / BN;
   const int kb_per_tap = ceil_div(a.Cin, bke);
   const int num_kb = a.KS * kb_per_tap;
+  const bool has_ln = a.ln_gamma != nullptr;
+  // Persistent form (see the kernel comment): bf16, staged epilogue only, short mainloops, more tiles than CTA slots.
+  const bool fast_like = a.out != nullptr && a.vt == nullptr && a.out_f32 == nullptr && a.dot_w == nullptr &&
+                         (a.residual == nullptr || (!a.residual_is_f32 && a.r_ld != 0));
+  bool persist = persist_mode() != 0 && es == 2 && fast_like && num_kb <= 16;
+  int BN = 0, ctas_per_sm = 2;
+  if (persist) {
+    if (has_ln) BN = (a.N <= 256 && a.N % 64 == 0) ? a.N : 0;
+    else BN = a.N % 128 == 0 ? 128 : ((a.N <= 128 && a.N % 64 == 0) ? a.N : 0);
+    if (BN == 0) persist = false;
+    else ctas_per_sm = 2 * tmem_cols_pow2(BN) <= 256 ? 2 : 1;     // two accumulators per CTA, 512 TMEM columns per SM
+    if (ctas_per_sm == 1 && persist_mode() != 2) persist = false;
+    if (persist && static_cast<long long>(m_tiles) * (a.N / BN) <= static_cast<long long>(ctas_per_sm) * num_sms()) persist = false;
+  }
+  if (!persist) BN = pick_bn(a, m_tiles);
+  SB_REQUIRE(BN > 0, "conv1d_tc: no valid N tile for N=%d", a.N);
+  const int n_tiles = a.N / BN;
+  const int total_tiles = m_tiles * n_tiles;
   const int stage_bytes = kAStageBytes + BN * 128;
-  int stages = smem_budget_bytes() / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages > num_kb) stages = num_kb;
-  if (stages < 2) stages = num_kb >= 2 ? 2 : 1;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/ + 4096 /*exchange*/;
+  const int staging_bytes = persist ? BN * es * kBM : 0;
+  const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/ + 4096 /*exchange*/;
+  int stages = ((persist ? (ctas_per_sm == 2 ? 113 : 226) * 1024 - staging_bytes - fixed_bytes : smem_budget_bytes())) / stage_bytes;
+  if (stages > (persist ? 4 : 8)) stages = persist ? 4 : 8;
+  if (!persist && stages > num_kb) stages = num_kb;
+  if (stages < 2) stages = (persist || num_kb >= 2) ? 2 : 1;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + staging_bytes + fixed_bytes;
   SB_REQUIRE(smem <= 227 * 1024, "conv1d_tc: smem %zu too large", smem);
 
   CUtensorMap tmA, tmB;
@@ -547,7 +632,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
     if (rc != 0) return rc;
   }
   // Coalesced epilogue I/O through the (by then idle) pipeline smem: needs whole 128-byte boxes and room for the tile.
-  const bool boxes_ok = (BN * es) % 128 == 0 && static_cast<size_t>(BN) * es * 128 <= static_cast<size_t>(stages) * stage_bytes;
+  const bool boxes_ok = (BN * es) % 128 == 0 && (persist || static_cast<size_t>(BN) * es * 128 <= static_cast<size_t>(stages) * stage_bytes);
   const bool stage_out = a.out != nullptr && boxes_ok;
   const bool stage_res = a.residual != nullptr && !a.residual_is_f32 && a.r_ld != 0 && boxes_ok;
   CUtensorMap tmOut = tmA, tmRes = tmA;
@@ -571,7 +656,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   EpiParams ep;
   ep.stage_out = stage_out ? 1 : 0;
   ep.stage_res = stage_res ? 1 : 0;
-  ep.dbg = (g_phase_buf != nullptr && m_tiles * n_tiles <= g_phase_cap) ? g_phase_buf : nullptr;
+  ep.dbg = (!persist && g_phase_buf != nullptr && total_tiles <= g_phase_cap) ? g_phase_buf : nullptr;
   ep.bias = a.bias; ep.act = a.act; ep.act2 = a.act2;
   ep.residual = a.residual; ep.r_bstride = a.r_bstride; ep.r_ld = a.r_ld; ep.res_f32 = a.residual_is_f32;
   ep.ln_gamma = a.ln_gamma; ep.ln_beta = a.ln_beta; ep.ln_eps = a.ln_eps;
@@ -581,27 +666,28 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   ep.out_f32 = a.out_f32; ep.of_bstride = a.of_bstride; ep.of_ld = a.of_ld;
   ep.vt = a.vt; ep.vt_col0 = a.vt_col0; ep.vt_bstride = a.vt_bstride; ep.vt_ld = a.vt_ld;
 
-  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, EpiParams, int, int, int, int, int, int, int, int);
-#define SB_K(A, L, F) conv1d_tc_kernel<T, A, L, F>
-  static const KernFn table[3][2][2] = {
-      {{SB_K(STYLER_ACT_NONE, false, false), SB_K(STYLER_ACT_NONE, false, true)},
-       {SB_K(STYLER_ACT_NONE, true, false), SB_K(STYLER_ACT_NONE, true, true)}},
-      {{SB_K(STYLER_ACT_RELU, false, false), SB_K(STYLER_ACT_RELU, false, true)},
-       {SB_K(STYLER_ACT_RELU, true, false), SB_K(STYLER_ACT_RELU, true, true)}},
-      {{SB_K(STYLER_ACT_TANH, false, false), SB_K(STYLER_ACT_TANH, false, true)},
-       {SB_K(STYLER_ACT_TANH, true, false), SB_K(STYLER_ACT_TANH, true, true)}}};
+  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, EpiParams, int, int, int, int, int, int, int, int, int);
+#define SB_K(A, L, F, P) conv1d_tc_kernel<T, A, L, F, P>
+#define SB_KROW(A, L) {{SB_K(A, L, false, false), nullptr}, {SB_K(A, L, true, false), SB_K(A, L, true, true)}}
+  static const KernFn table[3][2][2][2] = {{SB_KROW(STYLER_ACT_NONE, false), SB_KROW(STYLER_ACT_NONE, true)},
+                                           {SB_KROW(STYLER_ACT_RELU, false), SB_KROW(STYLER_ACT_RELU, true)},
+                                           {SB_KROW(STYLER_ACT_TANH, false), SB_KROW(STYLER_ACT_TANH, true)}};
+#undef SB_KROW
 #undef SB_K
-  static bool attr_set[3][2][2] = {};
-  const int ia = a.act, il = a.ln_gamma != nullptr ? 1 : 0;
+  static bool attr_set[3][2][2][2] = {};
+  const int ia = a.act, il = has_ln ? 1 : 0;
   const int ifast = (stage_out && a.vt == nullptr && a.out_f32 == nullptr && a.dot_w == nullptr &&
                      (a.residual == nullptr || stage_res)) ? 1 : 0;
-  KernFn kern = table[ia][il][ifast];
-  if (!attr_set[ia][il][ifast]) {
+  const int ip = persist ? 1 : 0;
+  SB_REQUIRE(!persist || ifast == 1, "conv1d_tc: internal: persistent form chosen for a non-staged epilogue");
+  KernFn kern = table[ia][il][ifast][ip];
+  if (!attr_set[ia][il][ifast][ip]) {
     SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[ia][il][ifast] = true;
+    attr_set[ia][il][ifast][ip] = true;
   }
-  SB_CUDA_OK(launch_pdl(kern, dim3(m_tiles * n_tiles), dim3(kThreads), smem, stream, tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles,
-                        tiles_per_utt, a.KS, a.pad, kb_per_tap, BN, stages));
+  const int grid = persist ? (total_tiles < ctas_per_sm * num_sms() ? total_tiles : ctas_per_sm * num_sms()) : total_tiles;
+  SB_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles,
+                        tiles_per_utt, a.KS, a.pad, kb_per_tap, BN, stages, total_tiles));
   SB_LAUNCH_OK();
   return 0;
 }

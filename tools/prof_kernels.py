@@ -74,6 +74,8 @@ def main():
     if dt == torch.bfloat16:   # the layout the engine uses in bf16: fused [B,T,768] buffer, V read row-major
         qkv = torch.empty(B, T, 768, device=dev, dtype=dt)
         ops.conv1d(x256, wqkv, bqkv, out=qkv, impl=ops.IMPL_TC)
+        cases["qkv_fused"] = (lambda: ops.conv1d(x256, wqkv, bqkv, out=qkv, impl=ops.IMPL_TC),
+                              2.0 * B * T * 768 * 256, B * T * (256 + 768) * es, "tensor")
         cases["attention_qkv"] = (lambda: ops.attention(qkv, None, lens, 4, out=ctx, impl=ops.IMPL_TC),
                                   4.0 * B * 4 * T * T * 64, B * T * 1024 * es, "tensor")
         # random-init-like score statistics (std ~0.4, as in the bench model): the running max is raised on the first key tile only
