@@ -32,6 +32,7 @@ extern "C" {
 #define STYLER_ACT_NONE 0
 #define STYLER_ACT_RELU 1
 #define STYLER_ACT_TANH 2
+#define STYLER_ACT_LRELU 3   /* max(v, act_slope * v), 0 < act_slope < 1 (hifigan/models.py:7,93-97,152) */
 
 int styler_version(void);
 const char* styler_last_error(void);
@@ -39,7 +40,7 @@ const char* styler_last_error(void);
 int64_t styler_launch_count(void);
 
 /* ---- Conv1d / Linear over channel-last activations with fused epilogue ----------------------------------
- * y[b,t,n] = act2( LN( act( sum_{tap,c} x[b,t+tap-pad,c] * w[tap][n][c] + bias[n] ) + residual[b,t,n] ) )
+ * y[b,t,n] = act2( LN( act( sum_{tap,c} x[b,t+tap*dilation-pad,c] * w[tap][n][c] + bias[n] ) + residual[b,t,n] ) )
  * then rows t >= lens[b] are zeroed (if lens), then optional row-dot.  Replaces nn.Linear / nn.Conv1d (+ReLU /
  * tanh / folded BatchNorm / residual + LayerNorm + masked_fill) at: transformer/SubLayers.py:41-43,58-59,72-76,
  * 84-87; Layers.py:29,32,121-130; modules.py:30-36,103-160,211-216,250-271,438-465,502-507; styler.py:31.
@@ -63,6 +64,11 @@ typedef struct {
                                                             transposed, vt[b][n-vt_col0][t] (dtype), instead of `out` */
   int32_t dtype;                                         /* STYLER_F32 | STYLER_BF16 */
   int32_t impl;                                          /* STYLER_IMPL_* */
+  int32_t dilation;                                      /* tap spacing in time steps; 0 or 1 = dense (nn.Conv1d dilation) */
+  float act_slope;                                       /* negative-side slope of STYLER_ACT_LRELU (act and act2) */
+  int32_t residual_inv_lrelu;                            /* 1: `residual` holds lrelu(r) (slope act_slope); r is recovered as
+                                                            (v < 0 ? v / act_slope : v) before the add, so a HiFi-GAN residual
+                                                            chain can be stored in activated form only */
 } styler_conv1d_args;
 int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream);
 
@@ -84,6 +90,12 @@ int styler_add_fwd(const void* a, int64_t a_bstride, int32_t a_ld, const void* a
                    int32_t a2_ld, const void* rowvec, int32_t rowvec_ld, const float* pos, void* out,
                    int64_t o_bstride, int32_t o_ld, int32_t B, int32_t T, int32_t C, int32_t dtype, void* stream);
 int styler_cast_fwd(const float* x, void* out, int64_t n, int32_t dtype, void* stream);
+
+/* ---- HiFi-GAN multi-receptive-field fusion + the leaky ReLU before the next layer (hifigan/models.py:152-162):
+ * inputs a, b, c (b, c optional) hold y_k = lrelu(x_k, slope_in); out = lrelu(mean_k x_k, slope_out), dtype io,
+ * n contiguous elements (multiple of 8). */
+int styler_lrelu_mean_fwd(const void* a, const void* b, const void* c, float slope_in, float slope_out, void* out,
+                          int64_t n, int32_t dtype, void* stream);
 
 /* ---- quantize_1D_torch index (utils.py:417-429): 0 if x<=0 else rint(x*255)+1; bit-exact integers ---- */
 int styler_quantize_index_fwd(const float* x, int32_t* idx, int64_t n, void* stream);

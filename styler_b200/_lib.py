@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libstyler_b200.so")
 
 F32, BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
@@ -32,12 +32,14 @@ class Conv1dArgs(ctypes.Structure):
         ("out_f32", c_vp), ("of_bstride", c_i64), ("of_ld", c_i32),
         ("vt", c_vp), ("vt_col0", c_i32), ("vt_bstride", c_i64), ("vt_ld", c_i32),
         ("dtype", c_i32), ("impl", c_i32),
+        ("dilation", c_i32), ("act_slope", c_f32), ("residual_inv_lrelu", c_i32),
     ]
 
 
 # name -> argtypes (restype int unless noted); mirrors include/styler_b200.h one to one
 _SIGNATURES = {
     "styler_conv1d_fwd": [ctypes.POINTER(Conv1dArgs), c_vp],
+    "styler_lrelu_mean_fwd": [c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_i64, c_i32, c_vp],
     "styler_attention_fwd": [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32,
                              c_i32, c_i32, c_vp],
     "styler_embed_pos_fwd": [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],

@@ -80,9 +80,10 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+__device__ __forceinline__ float apply_act(float v, int act, float slope = 0.f) {
   if (act == STYLER_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == STYLER_ACT_TANH) return tanhf(v);
+  if (act == STYLER_ACT_LRELU) return fmaxf(v, v * slope);
   return v;
 }
 

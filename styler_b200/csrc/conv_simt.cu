@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(styler_conv1d_args a, 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> n, ty -> m
   const T* xb = static_cast<const T*>(a.x) + b * a.x_bstride;
   const T* w = static_cast<const T*>(a.w);
+  const int dil = a.dilation > 1 ? a.dilation : 1;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(styler_conv1d_args a, 
         const int idx = threadIdx.x + i * 256;
         const int kk = idx & 15, m = idx >> 4;
         const int c = c0 + kk;
-        const int t = t0 + m + tap - a.pad;
+        const int t = t0 + m + tap * dil - a.pad;
         float va = 0.f, vb = 0.f;
         if (c < a.Cin && t >= 0 && t < a.T) va = DT<T>::ld(xb + static_cast<long long>(t) * a.x_ld + c);
         const int n = n0 + m;
@@ -65,13 +66,15 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(styler_conv1d_args a, 
       if (n >= a.N) continue;
       float v = acc[i][j];
       if (a.bias != nullptr) v += a.bias[n];
-      v = apply_act(v, a.act);
+      v = apply_act(v, a.act, a.act_slope);
       if (a.residual != nullptr) {
         const long long off = b * a.r_bstride + static_cast<long long>(t) * a.r_ld + n;
-        v += a.residual_is_f32 ? static_cast<const float*>(a.residual)[off] : DT<T>::ld(static_cast<const T*>(a.residual) + off);
+        float rv = a.residual_is_f32 ? static_cast<const float*>(a.residual)[off] : DT<T>::ld(static_cast<const T*>(a.residual) + off);
+        if (a.residual_inv_lrelu != 0 && rv < 0.f) rv = rv / a.act_slope;
+        v += rv;
       }
       if (fuse_tail) {
-        v = apply_act(v, a.act2);
+        v = apply_act(v, a.act2, a.act_slope);
         if (masked) v = 0.f;
       }
       if (a.vt != nullptr && n >= a.vt_col0) {
@@ -110,7 +113,7 @@ __global__ void row_tail_kernel(styler_conv1d_args a) {
   for (int n = lane; n < N; n += 32) {
     float v = rd(n);
     if (a.ln_gamma != nullptr) v = (v - mean) * rstd * a.ln_gamma[n] + a.ln_beta[n];
-    v = apply_act(v, a.act2);
+    v = apply_act(v, a.act2, a.act_slope);
     if (a.dot_w != nullptr) dot += v * a.dot_w[n];
     if (masked) v = 0.f;
     if (orow != nullptr) DT<T>::st(orow + n, v);
@@ -156,6 +159,10 @@ extern "C" int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream) {
              a->B, a->T, a->Cin, a->N, a->KS);
   SB_REQUIRE(a->out != nullptr || a->out_f32 != nullptr || a->dot_out != nullptr || a->vt != nullptr, "conv1d: no output");
   SB_REQUIRE(a->dtype == STYLER_F32 || a->dtype == STYLER_BF16, "conv1d: bad dtype %d", a->dtype);
+  SB_REQUIRE(a->dilation >= 0, "conv1d: bad dilation %d", a->dilation);
+  SB_REQUIRE((a->act != STYLER_ACT_LRELU && a->act2 != STYLER_ACT_LRELU && a->residual_inv_lrelu == 0) ||
+                 (a->act_slope > 0.f && a->act_slope < 1.f),
+             "conv1d: leaky ReLU needs 0 < act_slope < 1 (got %g)", static_cast<double>(a->act_slope));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int impl = a->impl;
   if (impl == STYLER_IMPL_AUTO) impl = conv1d_tc_supported(*a, nullptr) && a->B * a->T >= 64 ? STYLER_IMPL_TC : STYLER_IMPL_SIMT;

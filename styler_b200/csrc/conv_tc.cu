@@ -43,6 +43,8 @@ struct EpiParams {
   int stage_out, stage_res;   // 1: output rows / residual rows go through the freed pipeline smem with TMA (coalesced)
   const float* bias;
   int act, act2;
+  float slope, inv_slope;     // leaky ReLU negative-side slope and its reciprocal
+  int res_inv;                // residual is stored as lrelu(r): undo before the add
   const void* residual; long long r_bstride; int r_ld; int res_f32;
   const float* ln_gamma; const float* ln_beta; float ln_eps;
   const int64_t* lens;
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
                                                              const __grid_constant__ CUtensorMap tmRes,
                                                              const EpiParams ep, int Tlen, int n_tiles,
                                                              int tiles_per_utt, int KS, int pad, int kb_per_tap,
-                                                             int BN, int stages, int total_tiles) {
+                                                             int BN, int stages, int total_tiles, int dil) {
   static_assert(!PERSIST || FAST, "the persistent tile loop only exists for the staged (FAST) epilogue");
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int kBKE = 128 / sizeof(T);  // elements per 128-byte k-slice
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
           mbar_arrive_expect_tx(&full[s], stage_bytes);
           const int tap = kb / kb_per_tap, kc = (kb % kb_per_tap) * kBKE;
           uint8_t* sa = smem + s * stage_bytes;
-          tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap - pad, b);
+          tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap * dil - pad, b);
           tma_load_3d(sa + kAStageBytes, &tmB, &full[s], kc, n0, tap);
         }
         if (!PERSIST && (FAST ? ep.residual != nullptr : ep.stage_res != 0)) {
@@ -291,6 +293,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       } else {
         load16(res_row + c, rr);
       }
+      if (ep.res_inv != 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rr[i] = rr[i] < 0.f ? rr[i] * ep.inv_slope : rr[i];
+      }
     };
     auto store_out = [&](int c, const float (&v)[16]) {   // output columns c..c+15 (dtype T)
       if (FAST || st_out) {
@@ -313,6 +319,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       if constexpr (ACT == STYLER_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if constexpr (ACT == STYLER_ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * ep.slope);
       } else if constexpr (ACT == STYLER_ACT_TANH) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -326,11 +335,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
         }
       }
     };
-    const bool relu2 = ep.act2 == STYLER_ACT_RELU;     // post-LN activation: only none|relu on this path
+    const bool relu2 = ep.act2 == STYLER_ACT_RELU || ep.act2 == STYLER_ACT_LRELU;   // final activation: none | relu | lrelu
+    const float slope2 = ep.act2 == STYLER_ACT_LRELU ? ep.slope : 0.f;
     auto act2f = [&](float (&v)[16]) {
       if (relu2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope2);
       }
     };
 
@@ -658,6 +668,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   ep.stage_res = stage_res ? 1 : 0;
   ep.dbg = (!persist && g_phase_buf != nullptr && total_tiles <= g_phase_cap) ? g_phase_buf : nullptr;
   ep.bias = a.bias; ep.act = a.act; ep.act2 = a.act2;
+  ep.slope = a.act_slope; ep.inv_slope = a.act_slope > 0.f ? 1.0f / a.act_slope : 1.0f; ep.res_inv = a.residual_inv_lrelu;
   ep.residual = a.residual; ep.r_bstride = a.r_bstride; ep.r_ld = a.r_ld; ep.res_f32 = a.residual_is_f32;
   ep.ln_gamma = a.ln_gamma; ep.ln_beta = a.ln_beta; ep.ln_eps = a.ln_eps;
   ep.lens = a.lens;
@@ -666,15 +677,16 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   ep.out_f32 = a.out_f32; ep.of_bstride = a.of_bstride; ep.of_ld = a.of_ld;
   ep.vt = a.vt; ep.vt_col0 = a.vt_col0; ep.vt_bstride = a.vt_bstride; ep.vt_ld = a.vt_ld;
 
-  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, EpiParams, int, int, int, int, int, int, int, int, int);
+  using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, EpiParams, int, int, int, int, int, int, int, int, int, int);
 #define SB_K(A, L, F, P) conv1d_tc_kernel<T, A, L, F, P>
 #define SB_KROW(A, L) {{SB_K(A, L, false, false), nullptr}, {SB_K(A, L, true, false), SB_K(A, L, true, true)}}
-  static const KernFn table[3][2][2][2] = {{SB_KROW(STYLER_ACT_NONE, false), SB_KROW(STYLER_ACT_NONE, true)},
+  static const KernFn table[4][2][2][2] = {{SB_KROW(STYLER_ACT_NONE, false), SB_KROW(STYLER_ACT_NONE, true)},
                                            {SB_KROW(STYLER_ACT_RELU, false), SB_KROW(STYLER_ACT_RELU, true)},
-                                           {SB_KROW(STYLER_ACT_TANH, false), SB_KROW(STYLER_ACT_TANH, true)}};
+                                           {SB_KROW(STYLER_ACT_TANH, false), SB_KROW(STYLER_ACT_TANH, true)},
+                                           {SB_KROW(STYLER_ACT_LRELU, false), SB_KROW(STYLER_ACT_LRELU, true)}};
 #undef SB_KROW
 #undef SB_K
-  static bool attr_set[3][2][2][2] = {};
+  static bool attr_set[4][2][2][2] = {};
   const int ia = a.act, il = has_ln ? 1 : 0;
   const int ifast = (stage_out && a.vt == nullptr && a.out_f32 == nullptr && a.dot_w == nullptr &&
                      (a.residual == nullptr || stage_res)) ? 1 : 0;
@@ -687,7 +699,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   }
   const int grid = persist ? (total_tiles < ctas_per_sm * num_sms() ? total_tiles : ctas_per_sm * num_sms()) : total_tiles;
   SB_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles,
-                        tiles_per_utt, a.KS, a.pad, kb_per_tap, BN, stages, total_tiles));
+                        tiles_per_utt, a.KS, a.pad, kb_per_tap, BN, stages, total_tiles, a.dilation > 1 ? a.dilation : 1));
   SB_LAUNCH_OK();
   return 0;
 }
@@ -714,8 +726,9 @@ bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why) {
     return fail("residual not 16-byte aligned/strided");
   if (a.vt != nullptr && a.vt_col0 % 16 != 0) return fail("vt_col0 not a multiple of 16");
   if (a.T < 1 || a.B < 1) return fail("empty problem");
-  if (a.act < 0 || a.act > 2) return fail("bad act");
-  if (a.act2 != STYLER_ACT_NONE && a.act2 != STYLER_ACT_RELU) return fail("act2 must be none|relu on the tensor-core path");
+  if (a.act < 0 || a.act > 3) return fail("bad act");
+  if (a.act2 != STYLER_ACT_NONE && a.act2 != STYLER_ACT_RELU && a.act2 != STYLER_ACT_LRELU)
+    return fail("act2 must be none|relu|lrelu on the tensor-core path");
   return true;
 }
 

@@ -70,6 +70,29 @@ __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, lo
   if (i < n) DT<T>::st(out + i, x[i]);
 }
 
+// HiFi-GAN multi-receptive-field fusion (hifigan/models.py:154-161): the resblock outputs arrive in activated form
+// y_k = lrelu(x_k, slope_in) (the residual chain is stored that way, see styler_conv1d_args.residual_inv_lrelu); recover
+// x_k, average, and apply the leaky ReLU that precedes the next layer.  8 elements (16 B of bf16) per thread.
+template <typename T>
+__global__ void lrelu_mean_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, float inv_slope_in,
+                                  float scale, float slope_out, T* __restrict__ out, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float va[8], vb[8], vc[8], r[8];
+  load8(a + i * 8, va);
+  if (b != nullptr) load8(b + i * 8, vb);
+  if (c != nullptr) load8(c + i * 8, vc);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float s = va[k] < 0.f ? va[k] * inv_slope_in : va[k];
+    if (b != nullptr) s += vb[k] < 0.f ? vb[k] * inv_slope_in : vb[k];
+    if (c != nullptr) s += vc[k] < 0.f ? vc[k] * inv_slope_in : vc[k];
+    s *= scale;
+    r[k] = fmaxf(s, s * slope_out);
+  }
+  store8(out + i * 8, r);
+}
+
 // ---------------------------------------------------------------------------------------- quantise / one-hot conv
 __global__ void quantize_index_kernel(const float* __restrict__ x, int32_t* __restrict__ idx, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -398,6 +421,20 @@ extern "C" int styler_cast_fwd(const float* x, void* out, int64_t n, int32_t dty
   SB_REQUIRE(x && out && n > 0, "cast: bad arguments");
   SB_DISPATCH_DTYPE(dtype, T, (cast_kernel<T><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                                   x, static_cast<T*>(out), n)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_lrelu_mean_fwd(const void* a, const void* b, const void* c, float slope_in, float slope_out, void* out,
+                                     int64_t n, int32_t dtype, void* stream) {
+  SB_REQUIRE(a && out && n > 0 && n % 8 == 0, "lrelu_mean: bad arguments (n must be a multiple of 8)");
+  SB_REQUIRE(slope_in > 0.f && slope_in <= 1.f && slope_out >= 0.f && slope_out <= 1.f, "lrelu_mean: bad slopes");
+  SB_REQUIRE(b != nullptr || c == nullptr, "lrelu_mean: pass inputs in order (a, b, c)");
+  const int cnt = 1 + (b != nullptr) + (c != nullptr);
+  const long long n8 = n / 8;
+  SB_DISPATCH_DTYPE(dtype, T, (lrelu_mean_kernel<T><<<blocks_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                                  static_cast<const T*>(a), static_cast<const T*>(b), static_cast<const T*>(c), 1.0f / slope_in,
+                                  1.0f / cnt, slope_out, static_cast<T*>(out), n8)));
   SB_LAUNCH_OK();
   return 0;
 }

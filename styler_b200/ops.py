@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib as L
-from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, IMPL_AUTO, IMPL_SIMT, IMPL_TC  # noqa: F401
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, IMPL_AUTO, IMPL_SIMT, IMPL_TC  # noqa: F401
 
 
 def _v3(t, name="tensor"):
@@ -21,12 +21,13 @@ def _v3(t, name="tensor"):
 
 def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=None, residual_f32=None, ln=None, ln_eps=1e-5,
            act2=ACT_NONE, lens=None, dot=None, out=None, want_out=True, out_f32=None, vt=None, vt_col0=0,
-           impl=IMPL_AUTO):
+           impl=IMPL_AUTO, dilation=1, act_slope=0.0, residual_inv_lrelu=False):
     """y = epilogue(conv1d(x, w)) -- see styler_conv1d_fwd.  x [B,T,Cin]; w packed [KS,N,Cin] (same dtype as x).
 
     residual: [B,T,N] tensor added after `act`; residual_row: [B,N] row broadcast over t instead.
     ln: (gamma, beta) fp32 -> LayerNorm over N;  dot: (w[N] fp32, bias float) -> also returns the [B,T] fp32 row dot.
     vt: preallocated [B, N - vt_col0, Tpad] tensor receiving columns >= vt_col0 transposed.
+    dilation: tap spacing; act_slope: negative-side slope of ACT_LRELU; residual_inv_lrelu: `residual` holds lrelu(r).
     Returns out (dtype of x) unless want_out=False; with `dot`, returns (out_or_None, dot_out).
     """
     x, x_bs, x_ld = _v3(x, "x")
@@ -40,6 +41,7 @@ def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=
     a.w, a.N, a.KS, a.pad = w.data_ptr(), N, KS, pad
     a.bias = bias.data_ptr() if bias is not None else None
     a.act, a.act2 = act, act2
+    a.dilation, a.act_slope, a.residual_inv_lrelu = int(dilation), float(act_slope), 1 if residual_inv_lrelu else 0
     keep = [x, w, bias]
     if residual is not None:
         r, r_bs, r_ld = _v3(residual, "residual")
@@ -101,6 +103,18 @@ def attention(qk, vt, lens, n_head=4, *, out=None, impl=IMPL_AUTO):
                                          int(vt.stride(1)) if vt is not None else 0,
                                          L.ptr(lens), L.ptr(o), o_bs, o_ld, B, T, n_head, L.dtype_code(qk.dtype), impl,
                                          L.stream_ptr()), "attention")
+    return out
+
+
+def lrelu_mean(a, b=None, c=None, *, slope_in, slope_out, out=None):
+    """out = lrelu(mean_k x_k, slope_out) where the inputs hold y_k = lrelu(x_k, slope_in) (styler_lrelu_mean_fwd)."""
+    L.require_cuda(a)
+    ts = [t for t in (a, b, c) if t is not None]
+    assert all(t.is_contiguous() and t.shape == a.shape and t.dtype == a.dtype for t in ts)
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(L.lib().styler_lrelu_mean_fwd(L.ptr(a), L.ptr(b), L.ptr(c), float(slope_in), float(slope_out), L.ptr(out),
+                                          a.numel(), L.dtype_code(a.dtype), L.stream_ptr()), "lrelu_mean")
     return out
 
 
