@@ -157,6 +157,18 @@ int styler_bucket_embed_sum_fwd(const void* text, const void* spk, const void* n
 int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
                         int32_t* band_ws /* [2*n_mels] workspace: non-zero band of each filter row */, float* mel,
                         float* energy, void* stream);
+/* ---- Fused preprocessing front end (audio/tools.py:37-55 get_mel_from_wav; utils.py:412-416 energy_rescaling;
+ * the data/ preprocessing scripts store mel.T): the same kernel with the waveform scaling (y * in_scale, e.g. 1/max_wav_value) or the
+ * norm=False clamp to [-1,1] (clip_flag[b] = 1 if any sample was < -1, exactly what the reference's `clipt` detects)
+ * applied while the samples are staged, the mel written frame-major [B][F][n_mels] when frame_major != 0 (the layout
+ * STYLER.forward takes), and e_input[b][f] = clip((energy - e_min) / (e_max - e_min), 0, 1) written next to the raw
+ * energy when e_input != NULL.  clip_flag / e_input may be NULL. */
+int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
+                           int32_t* band_ws, float* mel, float* energy, float in_scale, int32_t clamp, int32_t* clip_flag,
+                           int32_t frame_major, float* e_input, float e_min, float e_max, void* stream);
+/* ---- f0_normalization / speaker_normalization (utils.py:387-409) over a padded batch of log-f0 contours [B][T]
+ * (unvoiced frames marked <= -1e10 keep their value; rows with undefined statistics and frames >= lens[b] are zero). */
+int styler_f0_norm_fwd(const float* f0, const int64_t* lens, float* out, int32_t B, int32_t T, void* stream);
 
 /* ---- Debug/tuning hook: when a device buffer of capacity_ctas*8 int64 is set, every tcgen05 conv launch with at most
  * capacity_ctas CTAs writes 8 clock64() phase stamps per CTA into it (tools/phase_timing.py); NULL disables. */

@@ -93,6 +93,71 @@ __global__ void lrelu_mean_kernel(const T* __restrict__ a, const T* __restrict__
   store8(out + i * 8, r);
 }
 
+// f0_normalization / speaker_normalization (utils.py:387-409) for a padded batch of log-f0 contours: per utterance, over
+// the voiced frames (f0 > -1e10) of its first lens[b] frames, z = (f0 - mean) / std / 4 clipped to [-1,1] and mapped to
+// [0,1]; unvoiced frames keep their value; if the statistics are undefined (no voiced frame, std == 0 - the reference
+// turns numpy's RuntimeWarning into an all-zero contour) the whole row is zero; frames >= lens[b] are zero (pad_1D).
+// Statistics in fp64 like numpy's (float64 mean / population std).  One CTA per utterance.
+__global__ void __launch_bounds__(256) f0_norm_kernel(const float* __restrict__ f0, const int64_t* __restrict__ lens,
+                                                      float* __restrict__ out, int Tn) {
+  __shared__ double s_sum[8], s_sq[8];
+  __shared__ long long s_cnt[8];
+  __shared__ double s_mean, s_std;
+  __shared__ int s_ok;
+  const int b = blockIdx.x;
+  const float* x = f0 + static_cast<long long>(b) * Tn;
+  float* o = out + static_cast<long long>(b) * Tn;
+  int len = lens != nullptr ? static_cast<int>(lens[b]) : Tn;
+  len = len < Tn ? len : Tn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto block_sum = [&](double v, double* sh) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    __syncthreads();
+    return t;
+  };
+  double sum = 0.0;
+  long long cnt = 0;
+  for (int t = threadIdx.x; t < len; t += 256)
+    if (x[t] > -1e10f) { sum += static_cast<double>(x[t]); ++cnt; }
+  const double tot = block_sum(sum, s_sum);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  long long n = 0;
+  for (int i = 0; i < 8; ++i) n += s_cnt[i];
+  const double mean = n > 0 ? tot / static_cast<double>(n) : 0.0;
+  double sq = 0.0;
+  for (int t = threadIdx.x; t < len; t += 256)
+    if (x[t] > -1e10f) { const double d = static_cast<double>(x[t]) - mean; sq += d * d; }
+  const double var = block_sum(sq, s_sq);
+  if (threadIdx.x == 0) {
+    s_mean = mean;
+    s_std = n > 0 ? sqrt(var / static_cast<double>(n)) : 0.0;
+    s_ok = (n > 0 && s_std > 0.0) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < Tn; t += 256) {
+    float r = 0.f;
+    if (t < len && s_ok) {
+      const float v = x[t];
+      if (v > -1e10f) {
+        double z = (static_cast<double>(v) - s_mean) / s_std / 4.0;
+        z = z < -1.0 ? -1.0 : (z > 1.0 ? 1.0 : z);
+        r = static_cast<float>((z + 1.0) / 2.0);
+      } else {
+        r = v;
+      }
+    }
+    o[t] = r;
+  }
+}
+
 // ---------------------------------------------------------------------------------------- quantise / one-hot conv
 __global__ void quantize_index_kernel(const float* __restrict__ x, int32_t* __restrict__ idx, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -435,6 +500,13 @@ extern "C" int styler_lrelu_mean_fwd(const void* a, const void* b, const void* c
   SB_DISPATCH_DTYPE(dtype, T, (lrelu_mean_kernel<T><<<blocks_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                                   static_cast<const T*>(a), static_cast<const T*>(b), static_cast<const T*>(c), 1.0f / slope_in,
                                   1.0f / cnt, slope_out, static_cast<T*>(out), n8)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_f0_norm_fwd(const float* f0, const int64_t* lens, float* out, int32_t B, int32_t T, void* stream) {
+  SB_REQUIRE(f0 && out && B > 0 && T > 0, "f0_norm: bad arguments");
+  f0_norm_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(f0, lens, out, T);
   SB_LAUNCH_OK();
   return 0;
 }

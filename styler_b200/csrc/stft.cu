@@ -67,7 +67,10 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* __restrict__ y, int N, int F,
                                                                   const float* __restrict__ basis,
                                                                   const int32_t* __restrict__ band, int n_mels,
-                                                                  float* __restrict__ mel, float* __restrict__ energy) {
+                                                                  float* __restrict__ mel, float* __restrict__ energy,
+                                                                  float in_scale, int clamp, int32_t* __restrict__ clip_flag,
+                                                                  int frame_major, float* __restrict__ e_input, float e_min,
+                                                                  float e_inv_range) {
   extern __shared__ __align__(16) uint8_t stft_smem[];
   float2* tw = reinterpret_cast<float2*>(stft_smem);                       // W_1024^k, k < 512
   float2* twA = tw + HALF;                                                 // W_64^k,  k < 8   (pass-2 base twiddles)
@@ -91,7 +94,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
       int src = f0 * HOP + i - NFFT / 2;
       if (src < 0) src = -src;
       if (src >= N) src = 2 * (N - 1) - src;
-      v[u] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
+      float x = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) * in_scale : 0.f;
+      if (clamp) {   // get_mel_from_wav(norm=False), audio/tools.py:44-49: clamp to [-1,1]; the flag only sees the NEGATIVE side
+        if (x < -1.f && clip_flag != nullptr) clip_flag[b] = 1;
+        x = fminf(fmaxf(x, -1.f), 1.f);
+      }
+      v[u] = x;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -222,23 +230,39 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   __syncthreads();
   // coalesced stores: FPB consecutive frames of one mel row are contiguous in mel[b][m][:]
   const int nf = min(FPB, F - f0);
-  for (int i = threadIdx.x; i < n_mels * FPB; i += kWarps * 32) {
-    const int m = i / FPB, fl = i % FPB;
-    if (fl < nf) mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = s_mel[m * MELLD + fl];
+  if (frame_major) {   // [B][F][n_mels]: the channel-last layout STYLER.forward takes as mel_target (the reference stores mel.T)
+    for (int i = threadIdx.x; i < n_mels * nf; i += kWarps * 32) {
+      const int fl = i / n_mels, m = i % n_mels;
+      mel[(static_cast<long long>(b) * F + f0 + fl) * n_mels + m] = s_mel[m * MELLD + fl];
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_mels * FPB; i += kWarps * 32) {
+      const int m = i / FPB, fl = i % FPB;
+      if (fl < nf) mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = s_mel[m * MELLD + fl];
+    }
   }
-  if (threadIdx.x < nf) energy[static_cast<long long>(b) * F + f0 + threadIdx.x] = s_en[threadIdx.x];
+  if (threadIdx.x < nf) {
+    const float e = s_en[threadIdx.x];
+    energy[static_cast<long long>(b) * F + f0 + threadIdx.x] = e;
+    if (e_input != nullptr)   // energy_rescaling, utils.py:412-416
+      e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = fminf(fmaxf((e - e_min) * e_inv_range, 0.f), 1.f);
+  }
 }
 
 }  // namespace
 }  // namespace sb
 
-extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
-                                   int32_t* band_ws, float* mel, float* energy, void* stream) {
+extern "C" int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
+                                      int32_t* band_ws, float* mel, float* energy, float in_scale, int32_t clamp,
+                                      int32_t* clip_flag, int32_t frame_major, float* e_input, float e_min, float e_max,
+                                      void* stream) {
   using namespace sb;
   SB_REQUIRE(y && mel_basis && band_ws && mel && energy, "stft_mel: null pointer");
   SB_REQUIRE(B > 0 && N > NFFT / 2 && n_mels > 0 && n_mels <= 256, "stft_mel: bad shape (B=%d N=%d n_mels=%d)", B, N, n_mels);
+  SB_REQUIRE(e_input == nullptr || e_max > e_min, "stft_mel: energy rescaling needs e_max > e_min");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int F = 1 + N / HOP;
+  if (clip_flag != nullptr) SB_CUDA_OK(cudaMemsetAsync(clip_flag, 0, sizeof(int32_t) * B, s));
   mel_band_kernel<<<ceil_div(n_mels, 8), 256, 0, s>>>(mel_basis, n_mels, band_ws);
   SB_LAUNCH_OK();
   dim3 grid(ceil_div(F, FPB), B);
@@ -251,7 +275,13 @@ extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const f
     SB_CUDA_OK(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr_set = true;
   }
-  stft_mel_kernel<<<grid, kWarps * 32, smem, s>>>(y, N, F, mel_basis, band_ws, n_mels, mel, energy);
+  stft_mel_kernel<<<grid, kWarps * 32, smem, s>>>(y, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag,
+                                                   frame_major, e_input, e_min, e_input != nullptr ? 1.0f / (e_max - e_min) : 0.f);
   SB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
+                                   int32_t* band_ws, float* mel, float* energy, void* stream) {
+  return styler_stft_mel_ex_fwd(y, B, N, mel_basis, n_mels, band_ws, mel, energy, 1.0f, 0, nullptr, 0, nullptr, 0.f, 1.f, stream);
 }

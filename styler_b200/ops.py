@@ -285,3 +285,31 @@ def stft_mel(y, mel_basis):
     L.check(L.lib().styler_stft_mel_fwd(L.ptr(y), B, N, L.ptr(mel_basis), n_mels, L.ptr(band), L.ptr(mel), L.ptr(energy),
                                         L.stream_ptr()), "stft_mel")
     return mel, energy
+
+
+def stft_mel_ex(y, mel_basis, *, in_scale=1.0, clamp=False, frame_major=False, energy_range=None):
+    """Fused front end (styler_stft_mel_ex_fwd): returns (mel, energy, clip_flag int32 [B] or None, e_input or None)."""
+    y = y.contiguous()
+    B, N = y.shape
+    n_mels = mel_basis.shape[0]
+    F = 1 + N // 256
+    mel = torch.empty((B, F, n_mels) if frame_major else (B, n_mels, F), device=y.device, dtype=torch.float32)
+    energy = torch.empty(B, F, device=y.device, dtype=torch.float32)
+    band = torch.empty(2 * n_mels, device=y.device, dtype=torch.int32)
+    flag = torch.empty(B, device=y.device, dtype=torch.int32) if clamp else None
+    e_in = torch.empty(B, F, device=y.device, dtype=torch.float32) if energy_range is not None else None
+    e_min, e_max = (float(energy_range[0]), float(energy_range[1])) if energy_range is not None else (0.0, 1.0)
+    L.check(L.lib().styler_stft_mel_ex_fwd(L.ptr(y), B, N, L.ptr(mel_basis), n_mels, L.ptr(band), L.ptr(mel), L.ptr(energy),
+                                           float(in_scale), 1 if clamp else 0, L.ptr(flag), 1 if frame_major else 0,
+                                           L.ptr(e_in), e_min, e_max, L.stream_ptr()), "stft_mel_ex")
+    return mel, energy, flag, e_in
+
+
+def f0_norm(f0, lens=None):
+    """f0_normalization (utils.py:387-409) over a padded [B,T] fp32 batch of log-f0 contours."""
+    f0 = f0.contiguous()
+    L.require_cuda(f0)
+    assert f0.dtype == torch.float32 and f0.dim() == 2
+    out = torch.empty_like(f0)
+    L.check(L.lib().styler_f0_norm_fwd(L.ptr(f0), L.ptr(lens), L.ptr(out), f0.shape[0], f0.shape[1], L.stream_ptr()), "f0_norm")
+    return out
