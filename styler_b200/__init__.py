@@ -2,7 +2,7 @@
 and the TacotronSTFT mel front end, behind the reference's Python surface.  See DESIGN.md / INTEGRATION.md."""
 from . import _lib  # noqa: F401
 
-__all__ = ["STYLER", "GraphedSTYLER", "TacotronSTFT", "ops", "hparams"]
+__all__ = ["STYLER", "GraphedSTYLER", "TacotronSTFT", "Generator", "ReferenceFrontEnd", "ops", "hparams"]
 
 
 def __getattr__(name):
@@ -15,7 +15,13 @@ def __getattr__(name):
     if name == "TacotronSTFT":
         from .stft import TacotronSTFT
         return TacotronSTFT
-    if name in ("ops", "hparams", "model", "stft", "engine", "dist"):
+    if name == "Generator":                      # HiFi-GAN vocoder (hifigan.Generator drop-in)
+        from .vocoder import Generator
+        return Generator
+    if name == "ReferenceFrontEnd":
+        from .frontend import ReferenceFrontEnd
+        return ReferenceFrontEnd
+    if name in ("ops", "hparams", "model", "stft", "engine", "dist", "vocoder", "frontend"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)
