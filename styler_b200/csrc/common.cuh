@@ -132,6 +132,8 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int conv1d_simt(const styler_conv1d_args& a, cudaStream_t s);
 int conv1d_tc(const styler_conv1d_args& a, cudaStream_t s);
 bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why);
+bool conv1d_win_supported(const styler_conv1d_args& a);   // conv_win.cu: few channels, many taps (HiFi-GAN resblocks)
+int conv1d_win(const styler_conv1d_args& a, cudaStream_t s);
 void set_phase_buffer(long long* buf, int cap);
 int attention_simt(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t vt_bs, int vt_ld,
                    const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int T, int H, int dtype,

@@ -88,6 +88,52 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(styler_conv1d_args a, 
   }
 }
 
+// N <= 4 outputs per time step (HiFi-GAN conv_post: 32 -> 1, k = 7; the 64x64 tile above would waste 63 of 64 columns):
+// one thread per output time step, the [256 + (KS-1)*dil][Cin] input window and the weights staged in smem as fp32,
+// HBM-bound by construction (every input row is read once per CTA).
+constexpr int kSmallT = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kSmallT) conv1d_smalln_kernel(styler_conv1d_args a, int tiles_per_utt, int win_rows) {
+  extern __shared__ float sm_small[];
+  float* xs = sm_small;                                   // [win_rows][Cin + 1]
+  const int ldx = a.Cin + 1;
+  float* ws = xs + static_cast<size_t>(win_rows) * ldx;   // [KS][N][Cin]
+  const int dil = a.dilation > 1 ? a.dilation : 1;
+  const int b = blockIdx.x / tiles_per_utt, t0 = (blockIdx.x % tiles_per_utt) * kSmallT;
+  const T* xb = static_cast<const T*>(a.x) + b * a.x_bstride;
+  for (int i = threadIdx.x; i < win_rows * a.Cin; i += kSmallT) {
+    const int r = i / a.Cin, c = i % a.Cin;
+    const int t = t0 + r - a.pad;
+    xs[r * ldx + c] = (t >= 0 && t < a.T) ? DT<T>::ld(xb + static_cast<long long>(t) * a.x_ld + c) : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.KS * a.N * a.Cin; i += kSmallT) ws[i] = DT<T>::ld(static_cast<const T*>(a.w) + i);
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= a.T) return;
+  const bool masked = a.lens != nullptr && t >= static_cast<int>(a.lens[b]);
+  for (int n = 0; n < a.N; ++n) {
+    float acc = 0.f;
+    for (int tap = 0; tap < a.KS; ++tap) {
+      const float* xr = xs + (threadIdx.x + tap * dil) * ldx;
+      const float* wr = ws + (tap * a.N + n) * a.Cin;
+      for (int c = 0; c < a.Cin; ++c) acc = fmaf(xr[c], wr[c], acc);
+    }
+    float v = acc + (a.bias != nullptr ? a.bias[n] : 0.f);
+    v = apply_act(v, a.act, a.act_slope);
+    if (a.residual != nullptr) {
+      const long long off = b * a.r_bstride + static_cast<long long>(t) * a.r_ld + n;
+      float rv = a.residual_is_f32 ? static_cast<const float*>(a.residual)[off] : DT<T>::ld(static_cast<const T*>(a.residual) + off);
+      if (a.residual_inv_lrelu != 0 && rv < 0.f) rv = rv / a.act_slope;
+      v += rv;
+    }
+    v = apply_act(v, a.act2, a.act_slope);
+    if (masked) v = 0.f;
+    if (a.out != nullptr) DT<T>::st(static_cast<T*>(a.out) + b * a.o_bstride + static_cast<long long>(t) * a.o_ld + n, v);
+    if (a.out_f32 != nullptr) a.out_f32[b * a.of_bstride + static_cast<long long>(t) * a.of_ld + n] = v;
+  }
+}
+
 // Warp per row: LayerNorm (two-pass, fp32), act2, row-dot, padding mask -- in place on the stored rows.
 template <typename T>
 __global__ void row_tail_kernel(styler_conv1d_args a) {
@@ -131,6 +177,19 @@ int launch(const styler_conv1d_args& a, cudaStream_t s) {
   SB_REQUIRE(!need_tail || a.out != nullptr || a.out_f32 != nullptr,
              "conv1d_simt: LayerNorm/dot epilogue needs an output buffer to stage rows");
   SB_REQUIRE(!need_tail || a.vt == nullptr, "conv1d_simt: LayerNorm/dot with vt is unsupported");
+  if (!need_tail && a.vt == nullptr && a.N <= 4 && a.Cin <= 128) {
+    const int dil = a.dilation > 1 ? a.dilation : 1;
+    const int win_rows = kSmallT + (a.KS - 1) * dil;
+    const size_t smem = (static_cast<size_t>(win_rows) * (a.Cin + 1) + static_cast<size_t>(a.KS) * a.N * a.Cin) * sizeof(float);
+    if (smem <= 200 * 1024) {
+      auto kern = conv1d_smalln_kernel<T>;
+      if (smem > 48 * 1024) SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      const int tpu = ceil_div(a.T, kSmallT);
+      kern<<<a.B * tpu, kSmallT, smem, s>>>(a, tpu, win_rows);
+      SB_LAUNCH_OK();
+      return 0;
+    }
+  }
   const int tiles_per_utt = ceil_div(a.T, TM);
   dim3 grid(a.B * tiles_per_utt, ceil_div(a.N, TN));
   conv1d_simt_kernel<T><<<grid, 256, 0, s>>>(a, tiles_per_utt, !need_tail);

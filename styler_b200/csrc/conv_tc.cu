@@ -737,6 +737,7 @@ void set_phase_buffer(long long* buf, int cap) { g_phase_buf = buf; g_phase_cap 
 int conv1d_tc(const styler_conv1d_args& a, cudaStream_t s) {
   const char* why = nullptr;
   SB_REQUIRE(conv1d_tc_supported(a, &why), "conv1d_tc: unsupported arguments: %s", why ? why : "?");
+  if (conv1d_win_supported(a)) return conv1d_win(a, s);
   if (a.dtype == STYLER_BF16) return launch<__nv_bfloat16>(a, s);
   return launch<float>(a, s);
 }

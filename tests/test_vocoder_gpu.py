@@ -53,6 +53,71 @@ def test_conv1d_dilated_lrelu_residual(cuda, dtype, impl, shape):
     assert rel_err(y2, y2_ref) < tol
 
 
+@pytest.mark.parametrize("shape", [(4, 10000, 32, 32, 11, 5), (4, 10000, 32, 32, 3, 1), (4, 10000, 64, 64, 7, 3), (5, 8100, 64, 64, 11, 5),
+                                   (4, 10000, 64, 32, 7, 1)],
+                         ids=["c32_k11_d5", "c32_k3_d1", "c64_k7_d3", "c64_k11_d5", "c64_n32_k7"])
+def test_conv1d_window_form(cuda, shape):
+    """Enough 128-step tiles (>= 2 per CTA slot) for the persistent window kernel (conv_win.cu): weights resident in smem,
+    one TMA window per tile, per-tap A descriptors at row offsets; ragged T, both epilogue forms of a resblock step."""
+    from styler_b200 import ops
+    B, T, Cin, N, KS, dil = shape
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(KS * 10 + dil + Cin)
+    y = torch.randn(B, T, Cin, generator=g)
+    y = torch.where(y < 0, y * 0.1, y)
+    w1 = (torch.rand(KS, N, Cin, generator=g) * 2 - 1) / math.sqrt(Cin * KS)
+    b1 = torch.randn(N, generator=g) * 0.1
+    q = lambda t: t.to(dtype).float()                                    # noqa: E731
+    lre = lambda t: torch.where(t < 0, t * 0.1, t)                       # noqa: E731
+    pad = (KS * dil - dil) // 2
+    z_ref = lre(F.conv1d(q(y).transpose(1, 2), q(w1).permute(1, 2, 0).contiguous(), b1, padding=pad, dilation=dil).transpose(1, 2))
+    yd = y.to(cuda, dtype)
+    z = ops.conv1d(yd, w1.to(cuda, dtype), b1.to(cuda), pad=pad, dilation=dil, act=ops.ACT_LRELU, act_slope=0.1, impl=ops.IMPL_TC)
+    torch.cuda.synchronize()
+    for b in range(B):
+        assert rel_err(z[b], z_ref[b]) < 1e-2, ("plain", b)
+    # edges of every utterance (zero padding through TMA out-of-range rows) and an interior tile boundary
+    for sl in (slice(0, 64), slice(T - 64, T), slice(128 * 3 - 32, 128 * 3 + 32)):
+        assert rel_err(z[:, sl], z_ref[:, sl]) < 1e-2
+    if Cin == N:
+        w2 = (torch.rand(KS, N, N, generator=g) * 2 - 1) / math.sqrt(N * KS)
+        b2 = torch.randn(N, generator=g) * 0.1
+        yq = q(y)
+        y2_ref = lre(F.conv1d(z.float().cpu().transpose(1, 2), q(w2).permute(1, 2, 0).contiguous(), b2,
+                              padding=(KS - 1) // 2).transpose(1, 2) + torch.where(yq < 0, yq / 0.1, yq))
+        y2 = ops.conv1d(z, w2.to(cuda, dtype), b2.to(cuda), pad=(KS - 1) // 2, residual=yd, residual_inv_lrelu=True,
+                        act2=ops.ACT_LRELU, act_slope=0.1, impl=ops.IMPL_TC)
+        torch.cuda.synchronize()
+        for b in range(B):
+            assert rel_err(y2[b], y2_ref[b]) < 1e-2, ("residual", b)
+        y3 = ops.conv1d(z, w2.to(cuda, dtype), b2.to(cuda), pad=(KS - 1) // 2, residual=yd, residual_inv_lrelu=True,
+                        act2=ops.ACT_LRELU, act_slope=0.1, impl=ops.IMPL_TC)
+        torch.cuda.synchronize()
+        assert torch.equal(y2, y3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("shape", [(2, 700, 32, 1, 7, 1, 2), (3, 300, 64, 4, 3, 2, 0), (1, 1000, 128, 2, 5, 3, 3)],
+                         ids=["conv_post_32_1_k7_tanh", "c64_n4_k3_d2", "c128_n2_k5_d3_lrelu"])
+def test_conv1d_small_n(cuda, dtype, shape):
+    """The one-thread-per-time-step CUDA-core kernel used for N <= 4 (HiFi-GAN conv_post + tanh, models.py:164-165)."""
+    from styler_b200 import ops
+    B, T, Cin, N, KS, dil, act = shape
+    g = torch.Generator().manual_seed(Cin + N)
+    x = torch.randn(B, T, Cin, generator=g)
+    w = (torch.rand(KS, N, Cin, generator=g) * 2 - 1) / math.sqrt(Cin * KS)
+    bias = torch.randn(N, generator=g) * 0.1
+    q = lambda t: t.to(dtype).float()                                    # noqa: E731
+    pad = (KS * dil - dil) // 2
+    ref = F.conv1d(q(x).transpose(1, 2), q(w).permute(1, 2, 0).contiguous(), bias, padding=pad, dilation=dil).transpose(1, 2)
+    ref = {0: ref, 2: torch.tanh(ref), 3: torch.where(ref < 0, ref * 0.1, ref)}[act]
+    out_f32 = torch.empty(B, T, N, device=cuda)
+    ops.conv1d(x.to(cuda, dtype), w.to(cuda, dtype), bias.to(cuda), pad=pad, dilation=dil, act=act, act_slope=0.1,
+               out_f32=out_f32, want_out=False, impl=ops.IMPL_SIMT)
+    torch.cuda.synchronize()
+    assert rel_err(out_f32, ref) < 2e-5
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
 def test_lrelu_mean(cuda, dtype):
     from styler_b200 import ops
