@@ -269,9 +269,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     // smem staging address of columns c..c+15 of this thread's row: box (c*es/128), 128-byte row r, 16-byte chunks XOR (r&7)
     uint8_t* stage_row = stg + r * 128;
     const int sw = r & 7;
-    auto stage_ptr = [&](int c, int chunk) -> uint8_t* {
-      const int byte0 = c * static_cast<int>(sizeof(T));
-      return stage_row + (byte0 / 128) * kAStageBytes + ((((byte0 % 128) / 16 + chunk) ^ sw) * 16);
+    auto stage_ptr = [&](int c, int chunk) -> uint8_t* {     // c is a multiple of 16 and every loop over c is unrolled by the
+      const int byte0 = c * static_cast<int>(sizeof(T));     // compiler only partially: keep the arithmetic to shifts and one XOR
+      return stage_row + (byte0 >> 7) * kAStageBytes + (((((byte0 & 127) >> 4) + chunk) ^ sw) << 4);
     };
     auto load_res = [&](int c, float (&rr)[16]) {       // residual columns c..c+15 of this thread's row
       if (FAST || st_res) {
@@ -350,11 +350,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     else if (PERSIST && it > 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // thread 64 has seen the previous store drain
     if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
 
-    float mean = 0.f, rstd = 1.f;
+    float mean = 0.f, rstd = 1.f, nmr = 0.f;   // nmr = -mean * rstd: (v - mean) * rstd = fma(v, rstd, nmr)
     if (has_ln) {
       // pass 1: v = act(acc + bias) + residual, parked back in TMEM; shifted sums for mean/variance.
       // Two 16-column chunks per iteration so TMEM and residual loads of both are in flight together.
-      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      float shift = 0.f;
+      float s1p[4] = {0.f, 0.f, 0.f, 0.f}, s2p[4] = {0.f, 0.f, 0.f, 0.f};   // 4 chains each: 16 dependent FADD/FFMA per chunk otherwise
       for (int c = c_begin; c < c_end; c += 32) {
         const bool two = c + 16 < c_end;
         uint32_t ra[16], rb[16];
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
           }
           if (c == c_begin) shift = v[0];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1 += d; s2 += d * d; ra[i] = __float_as_uint(v[i]); }
+          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1p[i & 3] += d; s2p[i & 3] = fmaf(d, d, s2p[i & 3]); ra[i] = __float_as_uint(v[i]); }
           tmem_st16(taddr + c, ra);
         }
         if (two) {
@@ -390,14 +391,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) v[i] += xb[i];
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1 += d; s2 += d * d; rb[i] = __float_as_uint(v[i]); }
+          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1p[i & 3] += d; s2p[i & 3] = fmaf(d, d, s2p[i & 3]); rb[i] = __float_as_uint(v[i]); }
           tmem_st16(taddr + c + 16, rb);
         }
       }
       tmem_st_wait();
       // combine the two half-row statistics (shifted sums are merged exactly; n_h = columns owned by half h)
       float* mine = s_x + (hf * 128 + r) * 4;
-      mine[0] = shift; mine[1] = s1; mine[2] = s2;
+      mine[0] = shift; mine[1] = (s1p[0] + s1p[1]) + (s1p[2] + s1p[3]); mine[2] = (s2p[0] + s2p[1]) + (s2p[2] + s2p[3]);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* h0 = s_x + r * 4;
       const float* h1 = s_x + (128 + r) * 4;
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       const float d0 = mean - h0[0], d1 = mean - h1[0];
       const float var = fmaxf((h0[2] - 2.f * d0 * h0[1] + n0f * d0 * d0 + h1[2] - 2.f * d1 * h1[1] + n1f * d1 * d1) * inv_n, 0.f);
       rstd = rsqrtf(var + ep.ln_eps);
+      nmr = -mean * rstd;
     }
     if (dbg != nullptr && threadIdx.x == 64 && has_ln) dbg[5] = clock64();
 
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
         ld16s(s_gamma + c, pa);
         ld16s(s_beta + c, pb);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf((__uint_as_float(ra[i]) - mean) * rstd, pa[i], pb[i]);
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(fmaf(__uint_as_float(ra[i]), rstd, nmr), pa[i], pb[i]);
       } else {
         ld16s(s_bias + c, pb);
 #pragma unroll
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
           ld16s(s_gamma + c + 16, pa);
           ld16s(s_beta + c + 16, pb);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaf((__uint_as_float(rb[i]) - mean) * rstd, pa[i], pb[i]);
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(fmaf(__uint_as_float(rb[i]), rstd, nmr), pa[i], pb[i]);
         } else {
           ld16s(s_bias + c + 16, pb);
 #pragma unroll

@@ -36,6 +36,11 @@ __global__ void mel_band_kernel(const float* __restrict__ basis, int n_mels, int
   if (lane == 0) { band[2 * m] = hi >= 0 ? lo : 0; band[2 * m + 1] = hi >= 0 ? hi + 1 : 0; }
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {   // MUFU.SQRT (2 ulp): the IEEE sqrtf costs ~8 instructions per magnitude
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
   return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
 }
@@ -86,27 +91,29 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   float* s_mel = reinterpret_cast<float*>(s_off + n_mels + 1);             // [n_mels][MELLD]
   const int b = blockIdx.y, f0 = blockIdx.x * FPB;
   const float* yb = y + static_cast<long long>(b) * N;
+  bool clipped = false;
   for (int i0 = 0; i0 < NSAMP; i0 += 4 * kWarps * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
     float v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 4; ++u) {                         // four independent loads in flight before anything is stored
       const int i = i0 + u * kWarps * 32 + threadIdx.x;
       int src = f0 * HOP + i - NFFT / 2;
       if (src < 0) src = -src;
       if (src >= N) src = 2 * (N - 1) - src;
-      float x = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) * in_scale : 0.f;
-      if (clamp) {   // get_mel_from_wav(norm=False), audio/tools.py:44-49: clamp to [-1,1]; the flag only sees the NEGATIVE side
-        if (x < -1.f && clip_flag != nullptr) clip_flag[b] = 1;
-        x = fminf(fmaxf(x, -1.f), 1.f);
-      }
-      v[u] = x;
+      v[u] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * kWarps * 32 + threadIdx.x;
-      if (i < NSAMP) samp[i] = v[u];
+      float x = v[u] * in_scale;
+      if (clamp) {   // get_mel_from_wav(norm=False), audio/tools.py:44-49: clamp to [-1,1]; the flag only sees the NEGATIVE side
+        clipped |= x < -1.f;
+        x = fminf(fmaxf(x, -1.f), 1.f);
+      }
+      if (i < NSAMP) samp[i] = x;
     }
   }
+  if (clipped && clip_flag != nullptr) clip_flag[b] = 1;   // one (benign, same-value) store per thread after the staging loop
   for (int k = threadIdx.x; k < HALF; k += kWarps * 32) {
     float sn, cs;
     sincospif(-static_cast<float>(k) / 512.0f, &sn, &cs);
@@ -205,8 +212,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
       const float xr = e.x + wo.x, xi = e.y + wo.y;                                      // X[k]
       const float yr = e.x - wo.x, yi = -e.y + wo.y;                                     // X[512-k] = conj(E) - conj(W^k O)
       const float p0 = xr * xr + xi * xi, p1 = yr * yr + yi * yi;
-      mg[k] = sqrtf(p0);
-      mg[HALF - k] = sqrtf(p1);
+      mg[k] = sqrt_approx(p0);
+      mg[HALF - k] = sqrt_approx(p1);
       esum += k == HALF / 2 ? p0 : p0 + p1;     // bin 256 is its own mirror
     }
     esum = warp_sum(esum);                      // energy: L2 norm over the 513 bins (stft.py:158)
