@@ -91,6 +91,15 @@ def main():
     h512b = torch.empty(B, T, 512, device=dev, dtype=dt)
     cases["postnet1"] = (lambda: ops.conv1d(h512, wp1, bp1, pad=2, act=ops.ACT_TANH, out=h512b, impl=ops.IMPL_TC),
                          2.0 * B * T * 512 * 5 * 512, B * T * 1024 * es, "tensor")
+    xa320 = rnd(B, T, 320)
+    wa, ba = rnd(5, 320, 320, scale=0.03), fp(320)
+    cases["audio_c320_k5"] = (lambda: ops.conv1d(xa320, wa, ba, pad=2, impl=ops.IMPL_TC),
+                              2.0 * B * T * 320 * 5 * 320, B * T * 640 * es, "tensor")
+    wpl, bpl = rnd(5, 80, 512, scale=0.02), fp(80)
+    melf = torch.zeros(B, T, 80, device=dev)
+    postf = torch.empty(B, T, 80, device=dev)
+    cases["postnet_last"] = (lambda: ops.conv1d(h512, wpl, bpl, pad=2, residual_f32=melf, out_f32=postf, want_out=False, impl=ops.IMPL_TC),
+                             2.0 * B * T * 80 * 5 * 512, B * T * (512 * es + 80 * 8), "tensor")
     wc3, bc3 = rnd(3, 256, 256, scale=0.04), fp(256)
     cases["pred_conv_ln"] = (lambda: ops.conv1d(x256, wc3, bc3, pad=1, act=ops.ACT_RELU, ln=ln, out=y256, impl=ops.IMPL_TC),
                              2.0 * B * T * 256 * 3 * 256, B * T * 512 * es, "tensor")
