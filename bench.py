@@ -184,6 +184,75 @@ def run_reference(args, rank, world):
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}))
 
 
+def vocoder_flops_per_utt(T, h):
+    """2 * MACs of every convolution of the HiFi-GAN generator (ConvTranspose1d at its true k taps)."""
+    fl, ch, t = 2.0 * T * 80 * h["upsample_initial_channel"] * 7, h["upsample_initial_channel"], T
+    for u, k in zip(h["upsample_rates"], h["upsample_kernel_sizes"]):
+        fl += 2.0 * t * ch * (ch // 2) * k
+        ch, t = ch // 2, t * u
+        for ks in h["resblock_kernel_sizes"]:
+            fl += 6 * 2.0 * t * ch * ch * ks
+    return fl + 2.0 * t * ch * 7
+
+
+def run_vocoder(args):
+    """Secondary workload: HiFi-GAN V1 generator forward, B=8 mel spectrograms of 1024 frames resident
+    in HBM -> waveform samples/s on one B200 (CUDA events), with the oracle port timed on the host cores on a bounded sample."""
+    from styler_b200 import _lib
+    from styler_b200 import synthetic as syn
+    from styler_b200.vocoder import CONFIG_V1, Generator
+    B, T = 8, 1024
+    dev = torch.device("cuda", 0)
+    voc = Generator(precision=args.precision)
+    voc.load_state_dict(syn.make_vocoder_state_dict(0))
+    voc = voc.to(dev).eval()
+    mel = syn.make_mel(B, T, seed=0).to(dev)
+    for _ in range(max(args.warmup, 3)):
+        voc(mel)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        wav = voc(mel)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.launch_count() - n0
+    fl = vocoder_flops_per_utt(T, CONFIG_V1) * B
+    peaks = load_peaks()
+    peak = peaks["tensor"] if args.precision == "bf16" else peaks["tensor"] / 2
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import hifigan_oracle as ho          # CPU-baseline leg only
+        torch.set_num_threads(host_threads())
+        frames = 64
+        sd, melc = ho.make_state_dict(0), ho.make_mel(1, frames, seed=0)
+        with torch.no_grad():
+            ho.generator_forward(sd, melc)
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                ho.generator_forward(sd, melc)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+        cpu = {"value": frames * 256 / best, "unit": "samples/s", "cores": host_threads(), "kind": "port",
+               "sample": "oracle port (torch CPU fp32), 1 utterance x %d mel frames, best of 3 (%.2f s each)" % (frames, best)}
+    print(json.dumps({
+        "metric": "waveform samples/sec (HiFi-GAN V1 generator forward)", "value": wav.numel() / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "HiFi-GAN V1 generator (hifigan/config.json), B=%d mel spectrograms x %d frames -> %d samples each; "
+                               "seeded synthetic weights" % (B, T, T * 256), "global_batch": B,
+                   "l2": "per-step activations (134 MB per 32-channel tensor) >> L2"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "whole forward (72 resblock convs + 4 transposed convs)", "achieved": fl / (ms * 1e-3) / 1e12,
+                     "peak": peak, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak,
+                     "peak_source": peaks["src"] + " bf16_tflops_sustained" + ("" if args.precision == "bf16" else " / 2 (tf32)"),
+                     "flops_per_launch": fl, "traffic": None},
+        "realtime_factor_22050Hz": wav.numel() / (ms * 1e-3) / 22050.0, "cpu_baseline": cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,7 +262,13 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the forward as one CUDA graph per resident batch (experiment)")
+    ap.add_argument("--workload", default="styler", choices=["styler", "vocoder"],
+                    help="styler = BASELINE.json's headline metric (default); vocoder = secondary HiFi-GAN line (single GPU)")
     args = ap.parse_args()
+    if args.workload == "vocoder":
+        args.steps = min(args.steps, 10)
+        run_vocoder(args)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
     from styler_b200 import dist as sdist

@@ -158,3 +158,35 @@ def make_inputs(B, L, Tr=None, seed=1234, ragged=False, d_mode="const8", frames=
         batch["p_target"] = (torch.rand(B, Tr, generator=g) * 900.0).masked_fill(pad_mel, 0)
         batch["e_target"] = (torch.rand(B, Tr, generator=g) * 600.0).masked_fill(pad_mel, 0)
     return batch
+
+
+# ---------------------------------------------------------------------------------------------------------------- vocoder
+def make_vocoder_state_dict(seed=0, h=None):
+    """Seeded HiFi-GAN generator weights in plain (remove_weight_norm) form with O(1) activations; same keys/shapes as
+    hifigan/models.py:104-148.  (The reference's own N(0, 0.01) init makes every output vanish.)"""
+    from .vocoder import CONFIG_V1
+    h = CONFIG_V1 if h is None else h
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def put(name, shape, fan_in, nbias, scale=1.0):
+        sd[name + ".weight"] = torch.randn(*shape, generator=g) / math.sqrt(fan_in) * scale
+        sd[name + ".bias"] = torch.randn(nbias, generator=g) * 0.05
+
+    ch = h["upsample_initial_channel"]
+    put("conv_pre", (ch, h["num_mels"], 7), h["num_mels"] * 7, ch)
+    nk = len(h["resblock_kernel_sizes"])
+    for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
+        put("ups.%d" % i, (ch, ch // 2, k), ch * k / u, ch // 2)
+        ch //= 2
+        for j, ks in enumerate(h["resblock_kernel_sizes"]):
+            for c in range(3):
+                put("resblocks.%d.convs1.%d" % (i * nk + j, c), (ch, ch, ks), ch * ks, ch)
+                put("resblocks.%d.convs2.%d" % (i * nk + j, c), (ch, ch, ks), ch * ks, ch)
+    put("conv_post", (1, ch, 7), ch * 7, 1, scale=0.5)
+    return sd
+
+
+def make_mel(B, T, seed=0):
+    g = torch.Generator().manual_seed(1000 + seed)
+    return torch.randn(B, 80, T, generator=g) * 2.0 - 4.0      # log-mel-like range
