@@ -72,6 +72,30 @@ typedef struct {
 } styler_conv1d_args;
 int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream);
 
+/* ---- One FFT block (transformer/Layers.py:26-34: MultiHeadAttention SubLayers.py:31-61 + PositionwiseFeedForward
+ * SubLayers.py:81-89) in one call: y = LN2(conv_k2(relu(conv_k1(y1))) + y1) masked, y1 = LN1(fc(attn(qkv(x))) + x) masked.
+ * Weights are the packed forms styler_conv1d_fwd takes ([KS][N][Cin], activation dtype; wqkv = W_q/temperature | W_k | W_v
+ * stacked on N).  x, y: [B][T][d_model] with explicit strides (y may alias a slice of a wider buffer, not x).
+ * workspace: styler_fftblock_workspace_bytes() bytes of device memory owned by the caller (256-byte aligned). */
+typedef struct {
+  int32_t d_model, d_inner, n_head;                      /* d_model == n_head * 64 */
+  const void* wqkv; const float* bqkv;                   /* [1][3*d_model][d_model], [3*d_model] */
+  const void* wfc; const float* bfc;                     /* [1][d_model][d_model] */
+  const float* ln1_gamma; const float* ln1_beta;
+  const void* w1; const float* b1; int32_t ks1;          /* [ks1][d_inner][d_model] */
+  const void* w2; const float* b2; int32_t ks2;          /* [ks2][d_model][d_inner] */
+  const float* ln2_gamma; const float* ln2_beta;
+  float ln_eps;
+} styler_fft_weights;
+int64_t styler_fftblock_workspace_bytes(int32_t B, int32_t T, int32_t d_model, int32_t d_inner, int32_t dtype);
+int styler_fftblock_fwd(const styler_fft_weights* w, const void* x, int64_t x_bstride, int32_t x_ld, void* y,
+                        int64_t y_bstride, int32_t y_ld, const int64_t* lens, int32_t B, int32_t T, int32_t dtype,
+                        int32_t impl, void* workspace, int64_t ws_bytes, void* stream);
+/* bench.py's roofline leg: CUDA events around every FFN first-conv launch issued by styler_fftblock_fwd with T >= min_T;
+ * _read synchronises them, returns count / summed ms / (B, T) of the last one and resets. */
+int styler_debug_ffn1_timing(int32_t enable, int32_t min_T);
+int styler_debug_ffn1_timing_read(float* total_ms, int32_t* launches, int64_t* last_B, int64_t* last_T);
+
 /* ---- Scaled-dot-product multi-head self-attention (transformer/Modules.py:14-25, SubLayers.py:44-56) ----
  * qk: [B][T][2*H*64] (Q columns then K columns, head h at h*64; 1/temperature already folded into Q),
  * vt: [B][H*64][vt_ld] (V transposed) -- or NULL, in which case V is read row-major from qk's columns [2*H*64, 3*H*64)

@@ -36,9 +36,27 @@ class Conv1dArgs(ctypes.Structure):
     ]
 
 
+class FftWeights(ctypes.Structure):
+    _fields_ = [
+        ("d_model", c_i32), ("d_inner", c_i32), ("n_head", c_i32),
+        ("wqkv", c_vp), ("bqkv", c_vp),
+        ("wfc", c_vp), ("bfc", c_vp),
+        ("ln1_gamma", c_vp), ("ln1_beta", c_vp),
+        ("w1", c_vp), ("b1", c_vp), ("ks1", c_i32),
+        ("w2", c_vp), ("b2", c_vp), ("ks2", c_i32),
+        ("ln2_gamma", c_vp), ("ln2_beta", c_vp),
+        ("ln_eps", c_f32),
+    ]
+
+
 # name -> argtypes (restype int unless noted); mirrors include/styler_b200.h one to one
 _SIGNATURES = {
     "styler_conv1d_fwd": [ctypes.POINTER(Conv1dArgs), c_vp],
+    "styler_fftblock_fwd": [ctypes.POINTER(FftWeights), c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32,
+                            c_i32, c_vp, c_i64, c_vp],
+    "styler_fftblock_workspace_bytes": [c_i32, c_i32, c_i32, c_i32, c_i32],
+    "styler_debug_ffn1_timing": [c_i32, c_i32],
+    "styler_debug_ffn1_timing_read": [c_vp, c_vp, c_vp, c_vp],
     "styler_lrelu_mean_fwd": [c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_i64, c_i32, c_vp],
     "styler_attention_fwd": [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32,
                              c_i32, c_i32, c_vp],
@@ -86,6 +104,7 @@ def lib():
     h.styler_version.restype = ctypes.c_int
     h.styler_last_error.restype = ctypes.c_char_p
     h.styler_launch_count.restype = ctypes.c_int64
+    h.styler_fftblock_workspace_bytes.restype = ctypes.c_int64
     _lib = h
     return h
 

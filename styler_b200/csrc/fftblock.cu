@@ -1,0 +1,153 @@
+// One FFT block (transformer/Layers.py:26-34 = SubLayers.py:31-61 MultiHeadAttention + :81-89 PositionwiseFeedForward) as a
+// single C-ABI call: the five kernels (QKV projection, flash attention, out-projection + residual + LayerNorm + mask,
+// Conv1d k9 + ReLU, Conv1d k1 + residual + LayerNorm + mask) are enqueued back to back on the caller's stream from native
+// code, with all intermediates carved from one caller-provided workspace.  Same kernels, one host call instead of five
+// (the Python host spends ~25 us per kernel call; ten FFT blocks per forward).
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace sb {
+namespace {
+
+inline size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct Ffn1Timing {
+  bool enabled = false;
+  int min_T = 0;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  int used = 0;                  // number of pairs recorded
+  long long last_B = 0, last_T = 0;
+} g_t;
+
+}  // namespace
+}  // namespace sb
+
+extern "C" int64_t styler_fftblock_workspace_bytes(int32_t B, int32_t T, int32_t d_model, int32_t d_inner, int32_t dtype) {
+  using namespace sb;
+  const size_t es = dtype == STYLER_BF16 ? 2 : 4;
+  const size_t rows = static_cast<size_t>(B) * T;
+  const size_t Tp = (static_cast<size_t>(T) + 7) / 8 * 8;
+  size_t n = 0;
+  if (dtype == STYLER_BF16) n += align_up(rows * 3 * d_model * es);                                          // fused qkv
+  else n += align_up(rows * 2 * d_model * es) + align_up(static_cast<size_t>(B) * d_model * Tp * es);        // qk + V^T
+  n += align_up(rows * d_model * es) * 2;                                                                      // ctx, y1
+  n += align_up(rows * d_inner * es);                                                                          // FFN hidden
+  return static_cast<int64_t>(n);
+}
+
+extern "C" int styler_fftblock_fwd(const styler_fft_weights* w, const void* x, int64_t x_bstride, int32_t x_ld, void* y,
+                                   int64_t y_bstride, int32_t y_ld, const int64_t* lens, int32_t B, int32_t T, int32_t dtype,
+                                   int32_t impl, void* workspace, int64_t ws_bytes, void* stream) {
+  using namespace sb;
+  SB_REQUIRE(w && x && y && workspace, "fftblock: null pointer");
+  SB_REQUIRE(B > 0 && T > 0, "fftblock: bad shape B=%d T=%d", B, T);
+  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "fftblock: bad dtype %d", dtype);
+  const int D = w->d_model, DI = w->d_inner, H = w->n_head;
+  SB_REQUIRE(D > 0 && DI > 0 && H > 0 && D == H * 64, "fftblock: d_model=%d must be n_head=%d x 64", D, H);
+  SB_REQUIRE(ws_bytes >= styler_fftblock_workspace_bytes(B, T, D, DI, dtype), "fftblock: workspace too small (%lld bytes)",
+             static_cast<long long>(ws_bytes));
+  const size_t es = dtype == STYLER_BF16 ? 2 : 4;
+  const size_t rows = static_cast<size_t>(B) * T;
+  const int Tp = (T + 7) / 8 * 8;
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  auto take = [&](size_t bytes) { uint8_t* r = p; p += align_up(bytes); return r; };
+  const bool v_rowmajor = dtype == STYLER_BF16;
+  void* qkv = take(rows * (v_rowmajor ? 3 : 2) * D * es);
+  void* vt = v_rowmajor ? nullptr : take(static_cast<size_t>(B) * D * Tp * es);
+  void* ctx = take(rows * D * es);
+  void* y1 = take(rows * D * es);
+  void* hid = take(rows * DI * es);
+  const int attn_impl = impl == STYLER_IMPL_SIMT ? STYLER_IMPL_SIMT : STYLER_IMPL_TC;
+  int rc;
+  {   // QKV projection (1/temperature folded into W_q at pack time)
+    styler_conv1d_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.x_bstride = x_bstride; a.x_ld = x_ld; a.B = B; a.T = T; a.Cin = D;
+    a.w = w->wqkv; a.N = 3 * D; a.KS = 1; a.bias = w->bqkv; a.dtype = dtype; a.impl = impl;
+    a.out = qkv;
+    if (v_rowmajor) { a.o_bstride = static_cast<int64_t>(T) * 3 * D; a.o_ld = 3 * D; }
+    else {
+      a.o_bstride = static_cast<int64_t>(T) * 2 * D; a.o_ld = 2 * D;
+      a.vt = vt; a.vt_col0 = 2 * D; a.vt_bstride = static_cast<int64_t>(D) * Tp; a.vt_ld = Tp;
+    }
+    if ((rc = styler_conv1d_fwd(&a, stream)) != 0) return rc;
+  }
+  if ((rc = styler_attention_fwd(qkv, static_cast<int64_t>(T) * (v_rowmajor ? 3 : 2) * D, (v_rowmajor ? 3 : 2) * D, vt,
+                                 static_cast<int64_t>(D) * Tp, Tp, lens, ctx, static_cast<int64_t>(T) * D, D, B, T, H, dtype,
+                                 attn_impl, stream)) != 0)
+    return rc;
+  {   // out-projection + residual + LayerNorm + padding mask
+    styler_conv1d_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = ctx; a.x_bstride = static_cast<int64_t>(T) * D; a.x_ld = D; a.B = B; a.T = T; a.Cin = D;
+    a.w = w->wfc; a.N = D; a.KS = 1; a.bias = w->bfc; a.dtype = dtype; a.impl = impl;
+    a.residual = x; a.r_bstride = x_bstride; a.r_ld = x_ld;
+    a.ln_gamma = w->ln1_gamma; a.ln_beta = w->ln1_beta; a.ln_eps = w->ln_eps; a.lens = lens;
+    a.out = y1; a.o_bstride = static_cast<int64_t>(T) * D; a.o_ld = D;
+    if ((rc = styler_conv1d_fwd(&a, stream)) != 0) return rc;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool timed = g_t.enabled && T >= g_t.min_T && g_t.used < 8192;
+  if (timed) {
+    while (static_cast<int>(g_t.ev.size()) < 2 * (g_t.used + 1)) {
+      cudaEvent_t e;
+      SB_CUDA_OK(cudaEventCreate(&e));
+      g_t.ev.push_back(e);
+    }
+    SB_CUDA_OK(cudaEventRecord(g_t.ev[2 * g_t.used], s));
+  }
+  {   // position-wise FFN, first conv (k = ks1) + ReLU: the dominant kernel
+    styler_conv1d_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = y1; a.x_bstride = static_cast<int64_t>(T) * D; a.x_ld = D; a.B = B; a.T = T; a.Cin = D;
+    a.w = w->w1; a.N = DI; a.KS = w->ks1; a.pad = (w->ks1 - 1) / 2; a.bias = w->b1; a.act = STYLER_ACT_RELU; a.dtype = dtype;
+    a.impl = impl;
+    a.out = hid; a.o_bstride = static_cast<int64_t>(T) * DI; a.o_ld = DI;
+    if ((rc = styler_conv1d_fwd(&a, stream)) != 0) return rc;
+  }
+  if (timed) {
+    SB_CUDA_OK(cudaEventRecord(g_t.ev[2 * g_t.used + 1], s));
+    g_t.used += 1;
+    g_t.last_B = B; g_t.last_T = T;
+  }
+  {   // second conv (k = ks2) + residual + LayerNorm + padding mask
+    styler_conv1d_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = hid; a.x_bstride = static_cast<int64_t>(T) * DI; a.x_ld = DI; a.B = B; a.T = T; a.Cin = DI;
+    a.w = w->w2; a.N = D; a.KS = w->ks2; a.pad = (w->ks2 - 1) / 2; a.bias = w->b2; a.dtype = dtype; a.impl = impl;
+    a.residual = y1; a.r_bstride = static_cast<int64_t>(T) * D; a.r_ld = D;
+    a.ln_gamma = w->ln2_gamma; a.ln_beta = w->ln2_beta; a.ln_eps = w->ln_eps; a.lens = lens;
+    a.out = y; a.o_bstride = y_bstride; a.o_ld = y_ld;
+    if ((rc = styler_conv1d_fwd(&a, stream)) != 0) return rc;
+  }
+  return 0;
+}
+
+// bench.py's roofline leg: CUDA events around every FFN-conv-k9 launch issued through styler_fftblock_fwd with T >= min_T.
+extern "C" int styler_debug_ffn1_timing(int32_t enable, int32_t min_T) {
+  sb::g_t.enabled = enable != 0;
+  sb::g_t.min_T = min_T;
+  sb::g_t.used = 0;
+  return 0;
+}
+
+// Synchronises the recorded events; returns their count, the summed milliseconds and the (B, T) of the last one; resets.
+extern "C" int styler_debug_ffn1_timing_read(float* total_ms, int32_t* launches, int64_t* last_B, int64_t* last_T) {
+  using namespace sb;
+  float tot = 0.f;
+  for (int i = 0; i < g_t.used; ++i) {
+    float ms = 0.f;
+    SB_CUDA_OK(cudaEventSynchronize(g_t.ev[2 * i + 1]));
+    SB_CUDA_OK(cudaEventElapsedTime(&ms, g_t.ev[2 * i], g_t.ev[2 * i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = g_t.used;
+  if (last_B) *last_B = g_t.last_B;
+  if (last_T) *last_T = g_t.last_T;
+  g_t.used = 0;
+  return 0;
+}

@@ -53,7 +53,6 @@ class Engine:
         import os
         self.use_streams = os.environ.get("STYLER_NO_STREAMS", "0") != "1"   # four audio-encoder branches on side streams
         self._streams = None
-        self.prof = None   # bench.py: list collecting (start_event, end_event, B, T) around the dominant kernel (FFN conv k9)
         self._pack({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
 
     # ------------------------------------------------------------------------------------------ packing
@@ -82,6 +81,7 @@ class Engine:
         W.w2, W.b2 = self._w(sd[f + "w_2.weight"]), self._f32(sd[f + "w_2.bias"])
         W.pad1 = (sd[f + "w_1.weight"].shape[2] - 1) // 2
         W.ln2 = (self._f32(sd[f + "layer_norm.weight"]), self._f32(sd[f + "layer_norm.bias"]))
+        W.c_struct = ops.make_fft_weights(W.wqkv, W.bqkv, W.wfc, W.bfc, W.ln1, W.w1, W.b1, W.w2, W.b2, W.ln2)   # styler_fft_weights
         return W
 
     def _pack_predictor(self, sd, p):
@@ -167,27 +167,9 @@ class Engine:
         return self._pos_cache[n]
 
     def fft_block(self, x, lens, W, out=None):
-        """transformer/Layers.py:26-34: MHA -> zero padded rows -> Conv1d FFN -> zero padded rows."""
-        B, T, _ = x.shape
-        if self.v_rowmajor:   # fused QKV rows; V consumed as an MN-major tensor-core operand (no transposed store)
-            qkv = ops.conv1d(x, W.wqkv, W.bqkv, impl=self.impl)
-            ctx = ops.attention(qkv, None, lens, 4, impl=self.attn_impl)
-        else:
-            Tp = (T + 7) // 8 * 8
-            qk = torch.empty(B, T, 512, device=x.device, dtype=self.dt)
-            vt = torch.empty(B, 256, Tp, device=x.device, dtype=self.dt)
-            ops.conv1d(x, W.wqkv, W.bqkv, out=qk, vt=vt, vt_col0=512, impl=self.impl)
-            ctx = ops.attention(qk, vt, lens, 4, impl=self.attn_impl)
-        y1 = ops.conv1d(ctx, W.wfc, W.bfc, residual=x, ln=W.ln1, lens=lens, impl=self.impl)
-        if self.prof is not None:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-        h = ops.conv1d(y1, W.w1, W.b1, pad=W.pad1, act=ACT_RELU, impl=self.impl)
-        if self.prof is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            self.prof.append((e0, e1, B, T))
-        return ops.conv1d(h, W.w2, W.b2, residual=y1, ln=W.ln2, lens=lens, out=out, impl=self.impl)
+        """transformer/Layers.py:26-34: MHA -> zero padded rows -> Conv1d FFN -> zero padded rows.  One native call
+        (styler_fftblock_fwd) enqueues the five kernels; intermediates live in one workspace allocation."""
+        return ops.fftblock(x, W.c_struct, lens, out=out, impl=self.impl)
 
     def text_encoder(self, src_seq, src_len, out=None):
         """transformer/Models.py:60-84."""

@@ -90,6 +90,36 @@ def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=
     return out
 
 
+def make_fft_weights(wqkv, bqkv, wfc, bfc, ln1, w1, b1, w2, b2, ln2, n_head=4, ln_eps=1e-5):
+    """Pack the pointers of one FFT block's (already packed, device-resident) weights into the C struct once; the
+    returned object keeps the tensors alive."""
+    fw = L.FftWeights()
+    fw.d_model, fw.d_inner, fw.n_head = wfc.shape[1], w1.shape[1], n_head
+    fw.wqkv, fw.bqkv, fw.wfc, fw.bfc = wqkv.data_ptr(), bqkv.data_ptr(), wfc.data_ptr(), bfc.data_ptr()
+    fw.ln1_gamma, fw.ln1_beta = ln1[0].data_ptr(), ln1[1].data_ptr()
+    fw.w1, fw.b1, fw.ks1 = w1.data_ptr(), b1.data_ptr(), w1.shape[0]
+    fw.w2, fw.b2, fw.ks2 = w2.data_ptr(), b2.data_ptr(), w2.shape[0]
+    fw.ln2_gamma, fw.ln2_beta, fw.ln_eps = ln2[0].data_ptr(), ln2[1].data_ptr(), ln_eps
+    fw._keep = (wqkv, bqkv, wfc, bfc, ln1, w1, b1, w2, b2, ln2)
+    return fw
+
+
+def fftblock(x, fw, lens, *, out=None, impl=IMPL_AUTO):
+    """One FFT block (styler_fftblock_fwd): x [B,T,d_model] -> y [B,T,d_model]; `out` may be a channel slice of a wider buffer."""
+    x, x_bs, x_ld = _v3(x, "x")
+    B, T, D = x.shape
+    assert D == fw.d_model
+    if out is None:
+        out = torch.empty(B, T, D, device=x.device, dtype=x.dtype)
+    o, o_bs, o_ld = _v3(out, "out")
+    code = L.dtype_code(x.dtype)
+    nbytes = int(L.lib().styler_fftblock_workspace_bytes(B, T, fw.d_model, fw.d_inner, code))
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    L.check(L.lib().styler_fftblock_fwd(ctypes.byref(fw), L.ptr(x), x_bs, x_ld, L.ptr(o), o_bs, o_ld, L.ptr(lens), B, T, code,
+                                        impl, L.ptr(ws), nbytes, L.stream_ptr()), "fftblock")
+    return out
+
+
 def attention(qk, vt, lens, n_head=4, *, out=None, impl=IMPL_AUTO):
     """ctx[B,T,H*64] = softmax(mask(Q K^T)) V ; qk [B,T,2*H*64] (Q pre-scaled) + vt [B,H*64,Tpad], or the fused
     qkv [B,T,3*H*64] with vt=None (V read row-major)."""
