@@ -42,6 +42,28 @@ def test_conv_args_struct_matches_header_order():
     assert names == [f[0] for f in _lib.Conv1dArgs._fields_], names
 
 
+def test_struct_layouts_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof of the two ABI structs as gcc lays them out from include/styler_b200.h == the ctypes mirrors."""
+    import ctypes
+    from styler_b200 import _lib
+    structs = {"styler_conv1d_args": _lib.Conv1dArgs, "styler_fft_weights": _lib.FftWeights}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "styler_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_dropin_surface():
     from oracle import styler_oracle as so
     from styler_b200 import STYLER
