@@ -91,3 +91,41 @@ def test_generator_refuses_cpu_tensors():
     from styler_b200.vocoder import Generator
     with pytest.raises(RuntimeError):
         Generator()(torch.zeros(1, 80, 4))
+
+
+def _real_checkpoint(tmp_path):
+    """The reference ships a pretrained generator (hifigan/generator_LJSpeech.pth.tar.zip); dev container only."""
+    import zipfile
+    z = "/root/reference/hifigan/generator_LJSpeech.pth.tar.zip"
+    if not os.path.isfile(z):
+        import pytest
+        pytest.skip("reference tree (and its pretrained vocoder checkpoint) not present")
+    zipfile.ZipFile(z).extractall(tmp_path)
+    return torch.load(os.path.join(tmp_path, "generator_LJSpeech.pth.tar"), map_location="cpu", weights_only=False)["generator"]
+
+
+def test_pretrained_checkpoint_loads_and_oracle_matches_live_reference(tmp_path):
+    """With the REAL LJSpeech weights (realistic dynamic range): the drop-in Generator accepts the checkpoint as saved
+    (234 weight_g / weight_v / bias tensors), folds it to exactly what the reference's remove_weight_norm() yields, and the
+    oracle reproduces the live reference generator on it."""
+    import contextlib
+    import io
+    import sys
+    sd = _real_checkpoint(tmp_path)
+    assert len(sd) == 234
+    sys.path.insert(0, "/root/reference")
+    import hifigan                                      # the reference package (torch only)
+    ref = hifigan.Generator(hifigan.AttrDict(ho.CONFIG_V1)).eval()
+    ref.load_state_dict(sd)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref.remove_weight_norm()
+    from styler_b200.vocoder import Generator
+    g = Generator()
+    g.load_state_dict(sd)
+    for k, v in ref.state_dict().items():
+        assert torch.allclose(g.state_dict()[k], v, rtol=1e-5, atol=1e-7), k
+    mel = ho.make_mel(1, 12, seed=3)
+    with torch.no_grad():
+        y_ref = ref(mel)
+        y_orc = ho.generator_forward(sd, mel)
+    assert (y_ref - y_orc).abs().max().item() < 1e-5 * max(1.0, y_ref.abs().max().item())
