@@ -162,16 +162,20 @@ int styler_length_regulator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, 
                                 int32_t* cum_ws, int32_t B, int32_t L, int32_t Tmax, int32_t C, int32_t dtype,
                                 void* stream);
 
-/* ---- bucketize + embedding + 4-way sum (modules.py:365-385):
+/* ---- bucketize + embedding + 4-way sum (modules.py:365-385, :299-307):
  * x[b,t,:] = text[b,t,:] + pitch_emb[bucket(p[b,t]*p_scale, pitch_bins)] + spk[b,t,:] + energy_emb[bucket(e*e_scale)]
  * (same summation order as the reference); optionally also x_noisy = x + noise; bucket = #bins < value
- * (torch.bucketize right=False); indices optionally returned (int32) for bit-exact tests.  When a scale
- * (p_control / e_control, modules.py:370,380) differs from 1 the scaled prediction is written back in place. */
+ * (torch.bucketize right=False); indices optionally returned (int32) for bit-exact tests.  The inputs are never written:
+ * the scaled predictions p*p_control / e*e_control the reference returns (modules.py:370,380) go to p_scaled / e_scaled
+ * (fp32 [B][T], may be NULL); pitch_emb_out / energy_emb_out (activation dtype, contiguous [B][T][C], may be NULL) receive
+ * the two embedding rows on their own, which is what predict_inference returns (modules.py:299-309).  out may be NULL
+ * (then text / spk / noise are not read). */
 int styler_bucket_embed_sum_fwd(const void* text, const void* spk, const void* noise, int64_t in_bstride,
-                                int32_t in_ld, float* p_val, float* e_val, float p_scale, float e_scale,
+                                int32_t in_ld, const float* p_val, const float* e_val, float p_scale, float e_scale,
                                 const float* pitch_bins, const float* energy_bins, int32_t nbins,
                                 const float* pitch_emb, const float* energy_emb, void* out, void* out_noisy,
-                                int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx, int32_t B, int32_t T,
+                                int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx, float* p_scaled,
+                                float* e_scaled, void* pitch_emb_out, void* energy_emb_out, int32_t B, int32_t T,
                                 int32_t C, int32_t dtype, void* stream);
 
 /* ---- TacotronSTFT.mel_spectrogram (audio/stft.py:51-79,141-160; audio_processing.py:80-86):
@@ -186,10 +190,15 @@ int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_b
  * norm=False clamp to [-1,1] (clip_flag[b] = 1 if any sample was < -1, exactly what the reference's `clipt` detects)
  * applied while the samples are staged, the mel written frame-major [B][F][n_mels] when frame_major != 0 (the layout
  * STYLER.forward takes), and e_input[b][f] = clip((energy - e_min) / (e_max - e_min), 0, 1) written next to the raw
- * energy when e_input != NULL.  clip_flag / e_input may be NULL. */
+ * energy when e_input != NULL.  clip_flag / e_input may be NULL.
+ * n_samples (int64 [B], device, may be NULL = every row holds N samples): the reference transforms every utterance ALONE
+ * (audio/tools.py:37-55 -> audio/stft.py:58-62), so row b of the zero-padded [B][N] batch is reflected around its own end
+ * n_samples[b] (must exceed n_fft/2) and yields 1 + n_samples[b]/hop frames; the remaining frames of the padded
+ * [.., F = 1 + N/hop] outputs are written as zeros (the collation padding of dataset.py:160-166). */
 int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
                            int32_t* band_ws, float* mel, float* energy, float in_scale, int32_t clamp, int32_t* clip_flag,
-                           int32_t frame_major, float* e_input, float e_min, float e_max, void* stream);
+                           int32_t frame_major, float* e_input, float e_min, float e_max, const int64_t* n_samples,
+                           void* stream);
 /* ---- f0_normalization / speaker_normalization (utils.py:387-409) over a padded batch of log-f0 contours [B][T]
  * (unvoiced frames marked <= -1e10 keep their value; rows with undefined statistics and frames >= lens[b] are zero). */
 int styler_f0_norm_fwd(const float* f0, const int64_t* lens, float* out, int32_t B, int32_t T, void* stream);

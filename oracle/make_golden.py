@@ -25,6 +25,9 @@ CASES = {
     "free_b2_l12_tr50": (0, dict(B=2, L=12, Tr=50, seed=14, ragged=False, d_mode=None), 5),
     "free_ragged_b3_l20_tr90": (1, dict(B=3, L=20, Tr=90, seed=15, ragged=True, d_mode=None), 3),
     "free_single_l50_tr400": (0, dict(B=1, L=50, Tr=400, seed=16, d_mode=None), 8),   # BASELINE configs[0]
+    # BASELINE configs[2] geometry (the bench shape): L=128 -> T=1024 > hp.max_seq_len, so the reference rebuilds the
+    # sinusoid table on the fly (transformer/Models.py:120-122); ragged text and reference-mel lengths
+    "tf_headline_b2_l128_t1024": (0, dict(B=2, L=128, seed=17, ragged=True, d_mode="const", frames=8), None),
 }
 
 
@@ -60,7 +63,8 @@ def build_case(name):
     return sd, so.make_inputs(**in_kw)
 
 
-def main():
+def main(only=None):
+    """only: optional list of case names to (re)generate; default all (+ the STFT golden)."""
     if not ref_shim.available():
         sys.exit("reference tree not available; goldens can only be generated in the dev container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -69,6 +73,8 @@ def main():
     ref = STYLER().eval()
     ref_keys = sorted(ref.state_dict().keys())
     for name in CASES:
+        if only and name not in only:
+            continue
         sd, batch = build_case(name)
         assert sorted(sd.keys()) == ref_keys, "state_dict surface mismatch"
         ref.load_state_dict(sd, strict=True)
@@ -97,6 +103,8 @@ def main():
         torch.save(flat, os.path.join(GOLDEN_DIR, name + ".pt"))
         print("wrote", name, {k: tuple(v.shape) for k, v in flat.items() if hasattr(v, "shape")})
 
+    if only:
+        return
     # ---- TacotronSTFT golden: reference conv-DFT path on CPU (audio/stft.py) -------------------
     Taco = ref_shim.load_reference_tacotron_stft()
     taco = Taco(1024, 256, 1024, 80, 22050, 0.0, 8000.0)
@@ -116,4 +124,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:] or None)

@@ -13,7 +13,20 @@
 namespace sb {
 
 static thread_local char g_err[512] = "";
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
+
+int num_sms() {
+  static std::atomic<int> cache[64];   // zero-initialised: 0 = not queried yet
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64) {
+    const int v = cache[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+  }
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  if (dev >= 0 && dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
 
 bool pdl_enabled() {
   static int v = -1;
@@ -111,5 +124,5 @@ int make_tmap(CUtensorMap* out, const void* base, int elem, int rank, const uint
 extern "C" {
 int styler_version(void) { return 100; }
 const char* styler_last_error(void) { return sb::g_err; }
-int64_t styler_launch_count(void) { return sb::g_launch_count; }
+int64_t styler_launch_count(void) { return sb::g_launch_count.load(); }
 }

@@ -420,11 +420,8 @@ int launch_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t 
     if (rc != 0) return rc;
   }
   auto kern = attention_tc_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
-    attr_set = true;
-  }
+  static DeviceFlags attr_set;
+  SB_OPT_IN_SMEM(attr_set, kern, C::smem);
   const int q_tiles = ceil_div(Tlen, kQ);
   SB_CUDA_OK(launch_pdl(kern, dim3(B * H * q_tiles), dim3(kThreadsTc), C::smem, s, tmQK, tmVT, lens, static_cast<T*>(ctx),
                         static_cast<long long>(ctx_bs), ctx_ld, Tlen, H, q_tiles, v_mn));

@@ -5,14 +5,39 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/styler_b200.h"
 
 namespace sb {
 
 // ---- error plumbing -------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
-extern long long g_launch_count;
-inline void count_launch(int n = 1) { g_launch_count += n; }
+extern std::atomic<long long> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+// Per-DEVICE one-shot state.  A process may drive several GPUs from several threads (nn.DataParallel, train.py:33 of the
+// reference): function attributes such as the >48 KB dynamic-smem opt-in are per device, so "already done" flags are kept
+// per device ordinal; a race at worst repeats an idempotent cudaFuncSetAttribute.
+inline int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
+}
+struct DeviceFlags {
+  std::atomic<unsigned long long> bits{0};
+  bool test(int dev) const { return dev >= 0 && dev < 64 && ((bits.load(std::memory_order_acquire) >> dev) & 1ull) != 0; }
+  void set(int dev) { if (dev >= 0 && dev < 64) bits.fetch_or(1ull << dev, std::memory_order_release); }
+};
+int num_sms();   // SM count of the current device (cached per device)
+
+#define SB_OPT_IN_SMEM(flags, kern, bytes)                                                                     \
+  do {                                                                                                         \
+    const int dev__ = ::sb::current_device();                                                                  \
+    if (!(flags).test(dev__)) {                                                                                \
+      SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes))); \
+      (flags).set(dev__);                                                                                      \
+    }                                                                                                          \
+  } while (0)
 
 #define SB_REQUIRE(cond, ...)          \
   do {                                 \

@@ -551,16 +551,6 @@ int persist_mode() {
   return v;
 }
 
-int num_sms() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
-  }
-  return sms;
-}
-
 int pick_bn(const styler_conv1d_args& a, int m_tiles) {
   if (a.ln_gamma != nullptr || a.dot_w != nullptr) return (a.N <= 256 && a.N % 16 == 0) ? a.N : 0;
   static int forced = -1;   // tuning override: STYLER_TC_BN
@@ -688,17 +678,14 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
                                            {SB_KROW(STYLER_ACT_LRELU, false), SB_KROW(STYLER_ACT_LRELU, true)}};
 #undef SB_KROW
 #undef SB_K
-  static bool attr_set[4][2][2][2] = {};
+  static DeviceFlags attr_set[4][2][2][2];
   const int ia = a.act, il = has_ln ? 1 : 0;
   const int ifast = (stage_out && a.vt == nullptr && a.out_f32 == nullptr && a.dot_w == nullptr &&
                      (a.residual == nullptr || stage_res)) ? 1 : 0;
   const int ip = persist ? 1 : 0;
   SB_REQUIRE(!persist || ifast == 1, "conv1d_tc: internal: persistent form chosen for a non-staged epilogue");
   KernFn kern = table[ia][il][ifast][ip];
-  if (!attr_set[ia][il][ifast][ip]) {
-    SB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[ia][il][ifast][ip] = true;
-  }
+  SB_OPT_IN_SMEM(attr_set[ia][il][ifast][ip], kern, 227 * 1024);
   const int grid = persist ? (total_tiles < ctas_per_sm * num_sms() ? total_tiles : ctas_per_sm * num_sms()) : total_tiles;
   SB_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles,
                         tiles_per_utt, a.KS, a.pad, kb_per_tap, BN, stages, total_tiles, a.dilation > 1 ? a.dilation : 1));

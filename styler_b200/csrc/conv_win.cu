@@ -182,16 +182,6 @@ int win_mode() {   // STYLER_CONV_WIN=0 sends these shapes back to conv_tc.cu (A
   return v;
 }
 
-int num_sms_win() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
-  }
-  return sms;
-}
-
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -211,7 +201,7 @@ bool conv1d_win_supported(const styler_conv1d_args& a) {
       (a.o_bstride * 2) % 16 != 0)
     return false;
   if (a.residual != nullptr && (!al16(a.residual) || (a.r_ld * 2) % 16 != 0 || (a.r_bstride * 2) % 16 != 0)) return false;
-  return static_cast<long long>(a.B) * ceil_div(a.T, kWM) >= 2LL * num_sms_win();   // persistent: needs enough tiles
+  return static_cast<long long>(a.B) * ceil_div(a.T, kWM) >= 2LL * num_sms();   // persistent: needs enough tiles
 }
 
 int conv1d_win(const styler_conv1d_args& a, cudaStream_t stream) {
@@ -243,13 +233,10 @@ int conv1d_win(const styler_conv1d_args& a, cudaStream_t stream) {
   ep.res_inv = a.residual_inv_lrelu;
   ep.lens = a.lens;
   ep.out = static_cast<__nv_bfloat16*>(a.out); ep.o_bstride = a.o_bstride; ep.o_ld = a.o_ld;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA_OK(cudaFuncSetAttribute(conv1d_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  static DeviceFlags attr_set;
+  SB_OPT_IN_SMEM(attr_set, conv1d_win_kernel, 200 * 1024);
   const int ctas_per_sm = smem <= 112 * 1024 ? 2 : 1;
-  const int cap = ctas_per_sm * num_sms_win();
+  const int cap = ctas_per_sm * num_sms();
   const int grid = total_tiles < cap ? total_tiles : cap;
   conv1d_win_kernel<<<grid, kWThreads, smem, stream>>>(tmX, tmW, ep, a.T, tiles_per_utt, total_tiles, a.KS, a.pad, dil, a.Cin,
                                                        a.N, win_rows);

@@ -5,6 +5,7 @@
 // (the Python host spends ~25 us per kernel call; ten FFT blocks per forward).
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -20,6 +21,7 @@ struct Ffn1Timing {
   std::vector<cudaEvent_t> ev;   // pairs (start, stop)
   int used = 0;                  // number of pairs recorded
   long long last_B = 0, last_T = 0;
+  std::mutex mu;                 // debug facility shared by every thread / stream that calls styler_fftblock_fwd
 } g_t;
 
 }  // namespace
@@ -90,6 +92,8 @@ extern "C" int styler_fftblock_fwd(const styler_fft_weights* w, const void* x, i
     if ((rc = styler_conv1d_fwd(&a, stream)) != 0) return rc;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::unique_lock<std::mutex> tlk(g_t.mu, std::defer_lock);
+  if (g_t.enabled) tlk.lock();   // enabled only by bench.py's roofline leg: serialises the event bookkeeping across threads
   const bool timed = g_t.enabled && T >= g_t.min_T && g_t.used < 8192;
   if (timed) {
     while (static_cast<int>(g_t.ev.size()) < 2 * (g_t.used + 1)) {
@@ -128,6 +132,7 @@ extern "C" int styler_fftblock_fwd(const styler_fft_weights* w, const void* x, i
 
 // bench.py's roofline leg: CUDA events around every FFN-conv-k9 launch issued through styler_fftblock_fwd with T >= min_T.
 extern "C" int styler_debug_ffn1_timing(int32_t enable, int32_t min_T) {
+  std::lock_guard<std::mutex> lk(sb::g_t.mu);
   sb::g_t.enabled = enable != 0;
   sb::g_t.min_T = min_T;
   sb::g_t.used = 0;
@@ -137,6 +142,7 @@ extern "C" int styler_debug_ffn1_timing(int32_t enable, int32_t min_T) {
 // Synchronises the recorded events; returns their count, the summed milliseconds and the (B, T) of the last one; resets.
 extern "C" int styler_debug_ffn1_timing_read(float* total_ms, int32_t* launches, int64_t* last_B, int64_t* last_T) {
   using namespace sb;
+  std::lock_guard<std::mutex> lk(g_t.mu);
   float tot = 0.f;
   for (int i = 0; i < g_t.used; ++i) {
     float ms = 0.f;

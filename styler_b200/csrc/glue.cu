@@ -400,10 +400,11 @@ __global__ void __launch_bounds__(256) lr_expand_kernel(const uint4* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) bucket_embed_sum_kernel(
     const T* __restrict__ text, const T* __restrict__ spk, const T* __restrict__ noise, long long in_bs, int in_ld,
-    float* __restrict__ p_val, float* __restrict__ e_val, float p_scale, float e_scale,
+    const float* __restrict__ p_val, const float* __restrict__ e_val, float p_scale, float e_scale,
     const float* __restrict__ pbins, const float* __restrict__ ebins, int nbins, const float* __restrict__ pemb,
     const float* __restrict__ eemb, T* __restrict__ out, T* __restrict__ out_noisy, long long o_bs, int o_ld,
-    int32_t* __restrict__ p_idx, int32_t* __restrict__ e_idx, int B, int Tn, int C) {
+    int32_t* __restrict__ p_idx, int32_t* __restrict__ e_idx, float* __restrict__ p_scaled, float* __restrict__ e_scaled,
+    T* __restrict__ pemb_out, T* __restrict__ eemb_out, int B, int Tn, int C) {
   extern __shared__ float sbins[];
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) { sbins[i] = pbins[i]; sbins[nbins + i] = ebins[i]; }
   __syncthreads();
@@ -418,20 +419,24 @@ __global__ void __launch_bounds__(256) bucket_embed_sum_kernel(
     return lo;
   };
   const int pi = lower(sbins, pv), ei = lower(sbins + nbins, ev);
-  if (lane == 0) {
+  if (lane == 0) {   // the inputs are never written: scaled predictions (modules.py:370,380) go to their own outputs
     if (p_idx != nullptr) p_idx[row] = pi;
     if (e_idx != nullptr) e_idx[row] = ei;
-    if (p_scale != 1.0f) p_val[row] = pv;
-    if (e_scale != 1.0f) e_val[row] = ev;
+    if (p_scaled != nullptr) p_scaled[row] = pv;
+    if (e_scaled != nullptr) e_scaled[row] = ev;
   }
   const long long in_off = b * in_bs + static_cast<long long>(t) * in_ld;
   const long long o_off = b * o_bs + static_cast<long long>(t) * o_ld;
   for (int c = lane * 8; c < C; c += 256) {
-    float tx[8], sp[8], pe[8], ee[8], v[8];
-    load8(text + in_off + c, tx);
-    load8(spk + in_off + c, sp);
+    float pe[8], ee[8];
     load8(pemb + static_cast<long long>(pi) * C + c, pe);
     load8(eemb + static_cast<long long>(ei) * C + c, ee);
+    if (pemb_out != nullptr) store8(pemb_out + row * C + c, pe);     // the embedding rows themselves (predict_inference)
+    if (eemb_out != nullptr) store8(eemb_out + row * C + c, ee);
+    if (out == nullptr) continue;
+    float tx[8], sp[8], v[8];
+    load8(text + in_off + c, tx);
+    load8(spk + in_off + c, sp);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = ((tx[i] + pe[i]) + sp[i]) + ee[i];
     store8(out + o_off + c, v);
@@ -606,18 +611,23 @@ extern "C" int styler_length_regulator_fwd(const void* x, int64_t x_bstride, int
 }
 
 extern "C" int styler_bucket_embed_sum_fwd(const void* text, const void* spk, const void* noise, int64_t in_bstride,
-                                           int32_t in_ld, float* p_val, float* e_val, float p_scale,
+                                           int32_t in_ld, const float* p_val, const float* e_val, float p_scale,
                                            float e_scale, const float* pitch_bins, const float* energy_bins, int32_t nbins,
                                            const float* pitch_emb, const float* energy_emb, void* out, void* out_noisy,
-                                           int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx, int32_t B,
-                                           int32_t T, int32_t C, int32_t dtype, void* stream) {
-  SB_REQUIRE(text && spk && p_val && e_val && pitch_bins && energy_bins && pitch_emb && energy_emb && out,
-             "bucket_embed_sum: null pointer");
+                                           int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx,
+                                           float* p_scaled, float* e_scaled, void* pitch_emb_out, void* energy_emb_out,
+                                           int32_t B, int32_t T, int32_t C, int32_t dtype, void* stream) {
+  SB_REQUIRE(p_val && e_val && pitch_bins && energy_bins && pitch_emb && energy_emb, "bucket_embed_sum: null pointer");
+  SB_REQUIRE(out == nullptr || (text != nullptr && spk != nullptr), "bucket_embed_sum: out needs text and spk");
+  SB_REQUIRE(out != nullptr || out_noisy == nullptr, "bucket_embed_sum: out_noisy needs out");
   SB_REQUIRE(out_noisy == nullptr || noise != nullptr, "bucket_embed_sum: out_noisy needs noise");
+  SB_REQUIRE(p_scaled != p_val && e_scaled != e_val, "bucket_embed_sum: the scaled outputs must not alias the inputs");
   SB_REQUIRE(B > 0 && T > 0 && C % 8 == 0 && in_ld % 8 == 0 && o_ld % 8 == 0 && in_bstride % 8 == 0 && o_bstride % 8 == 0 &&
                  nbins > 0 && nbins <= 4096, "bucket_embed_sum: bad shape");
-  SB_REQUIRE(al16(text) && al16(spk) && al16(out) && (noise == nullptr || al16(noise)) &&
-                 (out_noisy == nullptr || al16(out_noisy)) && al16(pitch_emb) && al16(energy_emb),
+  SB_REQUIRE((text == nullptr || al16(text)) && (spk == nullptr || al16(spk)) && (out == nullptr || al16(out)) &&
+                 (noise == nullptr || al16(noise)) && (out_noisy == nullptr || al16(out_noisy)) && al16(pitch_emb) &&
+                 al16(energy_emb) && (pitch_emb_out == nullptr || al16(pitch_emb_out)) &&
+                 (energy_emb_out == nullptr || al16(energy_emb_out)),
              "bucket_embed_sum: pointers must be 16-byte aligned");
   const long long rows = static_cast<long long>(B) * T;
   SB_DISPATCH_DTYPE(dtype, TT,
@@ -626,7 +636,8 @@ extern "C" int styler_bucket_embed_sum_fwd(const void* text, const void* spk, co
                         static_cast<const TT*>(text), static_cast<const TT*>(spk), static_cast<const TT*>(noise), in_bstride,
                         in_ld, p_val, e_val, p_scale, e_scale, pitch_bins,
                         energy_bins, nbins, pitch_emb, energy_emb, static_cast<TT*>(out), static_cast<TT*>(out_noisy),
-                        o_bstride, o_ld, p_idx, e_idx, B, T, C)));
+                        o_bstride, o_ld, p_idx, e_idx, p_scaled, e_scaled, static_cast<TT*>(pitch_emb_out),
+                        static_cast<TT*>(energy_emb_out), B, T, C)));
   SB_LAUNCH_OK();
   return 0;
 }

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
                                                                   float* __restrict__ mel, float* __restrict__ energy,
                                                                   float in_scale, int clamp, int32_t* __restrict__ clip_flag,
                                                                   int frame_major, float* __restrict__ e_input, float e_min,
-                                                                  float e_inv_range) {
+                                                                  float e_inv_range, const int64_t* __restrict__ n_samples) {
   extern __shared__ __align__(16) uint8_t stft_smem[];
   float2* tw = reinterpret_cast<float2*>(stft_smem);                       // W_1024^k, k < 512
   float2* twA = tw + HALF;                                                 // W_64^k,  k < 8   (pass-2 base twiddles)
@@ -91,6 +91,26 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   float* s_mel = reinterpret_cast<float*>(s_off + n_mels + 1);             // [n_mels][MELLD]
   const int b = blockIdx.y, f0 = blockIdx.x * FPB;
   const float* yb = y + static_cast<long long>(b) * N;
+  // Per-utterance length (audio/tools.py:37-55 runs every utterance alone): row b of the zero-padded batch holds Nb valid
+  // samples, is reflected around ITS OWN end and yields Fb = 1 + Nb/hop frames; frames >= Fb are written as zeros (the
+  // collation padding of dataset.py:160-166).  `N` stays the row stride and `F` the padded frame count of the outputs.
+  if (n_samples != nullptr) {
+    const long long nb = n_samples[b];
+    N = nb < N ? (nb > NFFT / 2 ? static_cast<int>(nb) : NFFT / 2 + 1) : N;
+  }
+  const int Fb = n_samples != nullptr ? min(F, 1 + N / HOP) : F;
+  if (f0 >= Fb) {   // block-uniform: this whole block of frames is padding
+    const int nf = min(FPB, F - f0);
+    for (int i = threadIdx.x; i < n_mels * nf; i += kWarps * 32) {
+      if (frame_major) mel[(static_cast<long long>(b) * F + f0) * n_mels + i] = 0.f;
+      else mel[(static_cast<long long>(b) * n_mels + i / nf) * F + f0 + i % nf] = 0.f;
+    }
+    if (threadIdx.x < nf) {
+      energy[static_cast<long long>(b) * F + f0 + threadIdx.x] = 0.f;
+      if (e_input != nullptr) e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = 0.f;
+    }
+    return;
+  }
   bool clipped = false;
   for (int i0 = 0; i0 < NSAMP; i0 += 4 * kWarps * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
     float v[4];
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   float* mg = mag + warp * MAGLD;
   auto slot = [](int i) { return i + (i >> 4); };
   for (int fl = warp; fl < FPB; fl += kWarps) {
-    if (f0 + fl >= F) break;                    // warp-uniform
+    if (f0 + fl >= Fb) break;                   // warp-uniform
     float2 v[2][8];
     // ---- pass 1 (Ns = 1): window, pack z[n] = x[2n] + i x[2n+1], butterfly, no twiddles
     {
@@ -237,22 +257,24 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   __syncthreads();
   // coalesced stores: FPB consecutive frames of one mel row are contiguous in mel[b][m][:]
   const int nf = min(FPB, F - f0);
+  const int nv = min(FPB, Fb - f0);            // valid frames of this block; [nv, nf) is per-utterance padding -> zeros
   if (frame_major) {   // [B][F][n_mels]: the channel-last layout STYLER.forward takes as mel_target (the reference stores mel.T)
     for (int i = threadIdx.x; i < n_mels * nf; i += kWarps * 32) {
       const int fl = i / n_mels, m = i % n_mels;
-      mel[(static_cast<long long>(b) * F + f0 + fl) * n_mels + m] = s_mel[m * MELLD + fl];
+      mel[(static_cast<long long>(b) * F + f0 + fl) * n_mels + m] = fl < nv ? s_mel[m * MELLD + fl] : 0.f;
     }
   } else {
     for (int i = threadIdx.x; i < n_mels * FPB; i += kWarps * 32) {
       const int m = i / FPB, fl = i % FPB;
-      if (fl < nf) mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = s_mel[m * MELLD + fl];
+      if (fl < nf) mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = fl < nv ? s_mel[m * MELLD + fl] : 0.f;
     }
   }
   if (threadIdx.x < nf) {
-    const float e = s_en[threadIdx.x];
+    const bool ok = static_cast<int>(threadIdx.x) < nv;
+    const float e = ok ? s_en[threadIdx.x] : 0.f;
     energy[static_cast<long long>(b) * F + f0 + threadIdx.x] = e;
     if (e_input != nullptr)   // energy_rescaling, utils.py:412-416
-      e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = fminf(fmaxf((e - e_min) * e_inv_range, 0.f), 1.f);
+      e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = ok ? fminf(fmaxf((e - e_min) * e_inv_range, 0.f), 1.f) : 0.f;
   }
 }
 
@@ -262,7 +284,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
 extern "C" int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
                                       int32_t* band_ws, float* mel, float* energy, float in_scale, int32_t clamp,
                                       int32_t* clip_flag, int32_t frame_major, float* e_input, float e_min, float e_max,
-                                      void* stream) {
+                                      const int64_t* n_samples, void* stream) {
   using namespace sb;
   SB_REQUIRE(y && mel_basis && band_ws && mel && energy, "stft_mel: null pointer");
   SB_REQUIRE(B > 0 && N > NFFT / 2 && n_mels > 0 && n_mels <= 256, "stft_mel: bad shape (B=%d N=%d n_mels=%d)", B, N, n_mels);
@@ -277,18 +299,16 @@ extern "C" int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, cons
                       sizeof(float) * kWarps * MAGLD + sizeof(float) * FPB + sizeof(float) * kBasisCap +
                       sizeof(int) * (3 * n_mels + 1) + sizeof(float) * n_mels * MELLD;
   SB_REQUIRE(smem <= 113 * 1024, "stft_mel: n_mels=%d needs %zu bytes of shared memory", n_mels, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA_OK(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    attr_set = true;
-  }
+  static DeviceFlags attr_set;
+  SB_OPT_IN_SMEM(attr_set, stft_mel_kernel, 113 * 1024);
   stft_mel_kernel<<<grid, kWarps * 32, smem, s>>>(y, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag,
-                                                   frame_major, e_input, e_min, e_input != nullptr ? 1.0f / (e_max - e_min) : 0.f);
+                                                   frame_major, e_input, e_min, e_input != nullptr ? 1.0f / (e_max - e_min) : 0.f,
+                                                   n_samples);
   SB_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,
                                    int32_t* band_ws, float* mel, float* energy, void* stream) {
-  return styler_stft_mel_ex_fwd(y, B, N, mel_basis, n_mels, band_ws, mel, energy, 1.0f, 0, nullptr, 0, nullptr, 0.f, 1.f, stream);
+  return styler_stft_mel_ex_fwd(y, B, N, mel_basis, n_mels, band_ws, mel, energy, 1.0f, 0, nullptr, 0, nullptr, 0.f, 1.f, nullptr, stream);
 }

@@ -137,17 +137,23 @@ class Engine:
                         (self._f32(sd[q + "d_bn1.weight"]), self._f32(sd[q + "d_bn1.bias"])),
                         self._f32(sd[q + "d_fc2.weight"]), self._f32(sd[q + "d_fc2.bias"]))
         w.mlp = {}
-        for n in ("duration", "pitch", "energy", "residual"):
+        for n in ("duration", "pitch", "energy", "residual", "pitch_norm"):
             q = "%s%s_linear." % (P, n)
             w.mlp[n] = (self._w(sd[q + "0.weight"]), self._f32(sd[q + "0.bias"]), self._w(sd[q + "2.weight"]),
                         self._f32(sd[q + "2.bias"]))
         w.tlu = (self._w(sd[P + "text_linear_up.0.weight"]), self._f32(sd[P + "text_linear_up.0.bias"]))
+        # the same packed weights by reference-module name: model.KernelMLP (the nn.Sequential sub-modules synthesize.py
+        # calls directly, :116-128,194-196) runs them through the GEMM kernels
+        w.seq = {"text_linear_down": [w.tld], "speaker_linear_p": [w.slp], "speaker_linear": [w.sl], "text_linear_up": [w.tlu]}
+        for n in w.mlp:
+            w.seq[n + "_linear"] = [w.mlp[n][0:2], w.mlp[n][2:4]]
         w.pred = {n: self._pack_predictor(sd, "%s%s_predictor." % (P, n)) for n in ("duration", "pitch", "energy")}
         w.pitch_bins, w.energy_bins = self._f32(sd[P + "pitch_bins"]), self._f32(sd[P + "energy_bins"])
         w.pitch_emb, w.energy_emb = self._f32(sd[P + "pitch_embedding.weight"]), self._f32(sd[P + "energy_embedding.weight"])
         w.mel = (self._w(sd["mel_linear.weight"]), self._f32(sd["mel_linear.bias"]))
         w.postnet = []
-        for j in range(5):   # fold eval-mode BatchNorm1d into the conv (Layers.py:91-119,121-130)
+        for j in range(5 if "postnet.convolutions.0.0.conv.weight" in sd else 0):   # (absent when use_postnet=False, styler.py:24-26)
+            # fold eval-mode BatchNorm1d into the conv (Layers.py:91-119,121-130)
             q = "postnet.convolutions.%d." % j
             cw, cb = sd[q + "0.conv.weight"].to(self.device, torch.float32), sd[q + "0.conv.bias"].to(self.device, torch.float32)
             g, be = sd[q + "1.weight"].to(self.device, torch.float32), sd[q + "1.bias"].to(self.device, torch.float32)
@@ -256,6 +262,8 @@ class Engine:
             mel_t = mel
         else:
             mel_t = ops.conv1d(h, self.w.mel[0], self.w.mel[1], out_f32=mel, impl=self.impl)
+        if not self.w.postnet:                       # use_postnet=False (styler.py:33-36): mel_output_postnet = mel_output
+            return mel, mel
         p = mel_t
         for j in range(4):
             p = ops.conv1d(p, self.w.postnet[j][0], self.w.postnet[j][1], pad=2, act=ACT_TANH, impl=self.impl)
@@ -315,9 +323,14 @@ class Engine:
         # clean and noisy decoder inputs land in one [2B,T,256] buffer so both decodes run as a single batched pass
         B = encT.shape[0]
         xx = torch.empty(2 * B, T, 256, device=encT.device, dtype=self.dt)
-        x, x_noisy, _, _ = ops.bucket_embed_sum(encT[..., 0:256], encT[..., 512:768], encT[..., 1024:1280], p_val, e_val,
-                                                p_scale, e_scale, w.pitch_bins, w.energy_bins, w.pitch_emb, w.energy_emb,
-                                                want_noisy=True, out=xx[:B], out_noisy=xx[B:])
+        scaled = p_scale != 1.0 or e_scale != 1.0      # the reference returns prediction * control (modules.py:370,380)
+        res = ops.bucket_embed_sum(encT[..., 0:256], encT[..., 512:768], encT[..., 1024:1280], p_val, e_val,
+                                   p_scale, e_scale, w.pitch_bins, w.energy_bins, w.pitch_emb, w.energy_emb,
+                                   want_noisy=True, out=xx[:B], out_noisy=xx[B:], want_scaled=scaled)
+        x, x_noisy = res[0], res[1]
+        if scaled:
+            p_pred = res[4] if p_target is None else p_pred
+            e_pred = res[5] if e_target is None else e_pred
         self._xx = xx
         return x, x_noisy, encT, p_pred, e_pred, mel_len
 

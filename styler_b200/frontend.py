@@ -33,14 +33,18 @@ class ReferenceFrontEnd(nn.Module):
         return self.mel_basis.device
 
     @torch.no_grad()
-    def mel_energy_from_wav(self, wav, norm=True, frame_major=False):
+    def mel_energy_from_wav(self, wav, norm=True, frame_major=False, n_samples=None):
         """Batched get_mel_from_wav: wav [B,N] (int16 scale if norm) -> (mel [B,80,F] or [B,F,80], energy [B,F],
-        e_input [B,F], clipt bool [B])."""
+        e_input [B,F], clipt bool [B]).  With `n_samples` (int64 [B]) every row of the zero-padded batch is transformed as
+        the reference transforms it alone (audio/tools.py:37-55): reflected around its own end, 1 + n_samples[b] // 256
+        frames, zeros beyond."""
         dev = self._dev()
         wav = wav.to(dev, torch.float32)
+        if n_samples is not None:
+            n_samples = torch.as_tensor(n_samples, dtype=torch.int64).to(dev)
         mel, energy, flag, e_in = ops.stft_mel_ex(wav, self.mel_basis, in_scale=(1.0 / self.max_wav_value) if norm else 1.0,
                                                   clamp=not norm, frame_major=frame_major,
-                                                  energy_range=(self.energy_min, self.energy_max))
+                                                  energy_range=(self.energy_min, self.energy_max), n_samples=n_samples)
         clipt = flag.bool() if flag is not None else torch.zeros(wav.shape[0], dtype=torch.bool, device=dev)
         return mel, energy, e_in, clipt
 
@@ -58,11 +62,12 @@ class ReferenceFrontEnd(nn.Module):
         dev = self._dev()
         n_samples = torch.as_tensor(n_samples, dtype=torch.int64)
         mel_len = (1 + n_samples // 256).to(dev)
-        mel, energy, e_in, clipt = self.mel_energy_from_wav(wav, norm=norm, frame_major=True)
+        if int(n_samples.min()) <= 512 or int(n_samples.max()) > wav.shape[1]:
+            raise ValueError("n_samples must lie in (n_fft/2, N]: reflect padding needs more than 512 samples per utterance")
+        # per-utterance reflect padding / frame count / zero tail (the collation padding of dataset.py:160-166) happen in the kernel
+        mel, energy, e_in, clipt = self.mel_energy_from_wav(wav, norm=norm, frame_major=True, n_samples=n_samples)
         F = mel.shape[1]
-        assert logf0.shape[1] <= F and int(mel_len.max()) <= F
+        assert logf0.shape[1] <= F
         p_norm = torch.zeros(mel.shape[0], F, device=dev, dtype=torch.float32)
-        p_norm[:, :logf0.shape[1]] = self.f0_normalization(logf0, mel_len.clamp(max=logf0.shape[1]))
-        pad = torch.arange(F, device=dev).unsqueeze(0) >= mel_len.unsqueeze(1)          # collation padding (dataset.py:160-166)
-        return dict(mel_target=mel.masked_fill(pad.unsqueeze(-1), 0.0), p_norm=p_norm.masked_fill(pad, 0.0),
-                    e_input=e_in.masked_fill(pad, 0.0), energy=energy.masked_fill(pad, 0.0), mel_len=mel_len, clipt=clipt)
+        p_norm[:, :logf0.shape[1]] = self.f0_normalization(logf0, mel_len.clamp(max=logf0.shape[1]))   # zero beyond lens[b]
+        return dict(mel_target=mel, p_norm=p_norm, e_input=e_in, energy=energy, mel_len=mel_len, clipt=clipt)

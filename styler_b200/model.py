@@ -6,6 +6,7 @@ The torch.nn modules below are PARAMETER CONTAINERS only (they give `load_state_
 reference's exact key surface, Appendix D of SURVEY.md); none of their torch forward code runs on the product path.
 Training (backward, dropout, batch-stat BatchNorm) is out of scope: calling forward in training mode raises.
 """
+import weakref
 from collections import OrderedDict
 
 import numpy as np
@@ -82,6 +83,41 @@ class PostNet(_Container):                  # transformer/Layers.py:67-119
                                            for i in range(n)])
 
 
+class KernelMLP(nn.Sequential):
+    """`nn.Sequential(Linear, ReLU[, Linear, ReLU])` of the reference (modules.py:207-216,250-265) with the SAME state_dict
+    keys (`0.weight`, `2.weight`, ...) whose forward runs the library's GEMM kernels (Linear + bias + ReLU fused) instead of
+    torch's: synthesize.py calls these modules directly when it recombines encodings (`self_.pitch_linear(p_down + s_down)`
+    :118-119,196; `style_encoder.speaker_linear_p / speaker_linear(speaker_embed)` :194-195).  Takes [.., Cin] fp32 or
+    activation-dtype tensors, returns fp32 like the reference."""
+
+    def __init__(self, owner, key, dims):
+        mods = []
+        for i, o in zip(dims[:-1], dims[1:]):
+            mods += [nn.Linear(i, o), nn.ReLU()]
+        super().__init__(*mods)
+        object.__setattr__(self, "_owner", owner)
+        self._key = key
+
+    def forward(self, x):
+        from . import ops
+        eng = self._owner._engine_for(x)
+        layers = eng.w.seq[self._key]
+        lead = x.shape[:-1]
+        h = x.to(eng.device).reshape(1, -1, x.shape[-1]) if x.dim() != 3 else x.to(eng.device)
+        h = eng._act(h) if h.dtype != eng.dt else h.contiguous()
+        with torch.cuda.device(eng.device):
+            for j, (w, b) in enumerate(layers):
+                if j + 1 < len(layers):
+                    h = ops.conv1d(h, w, b, act=ops.ACT_RELU, impl=eng.impl)
+                else:
+                    out = torch.empty(h.shape[0], h.shape[1], w.shape[1], device=eng.device, dtype=torch.float32)
+                    if eng.dt == torch.float32:
+                        ops.conv1d(h, w, b, act=ops.ACT_RELU, out=out, impl=eng.impl)
+                    else:
+                        ops.conv1d(h, w, b, act=ops.ACT_RELU, out_f32=out, want_out=False, impl=eng.impl)
+        return out.reshape(*lead, out.shape[-1])
+
+
 class EncoderInput(tuple):
     """What `StyleEncoder.encoder_input_cat` returns here: (mel_target, p_index, e_index, mel_aug) instead of the
     reference's dense [B,674,Tr] one-hot tensor (modules.py:218-223); `AudioEncoder.forward` consumes it."""
@@ -112,9 +148,9 @@ class StyleEncoder(_Container):             # modules.py:204-216
         object.__setattr__(self, "_owner", owner)
         self.text_encoder = Encoder()
         self.audio_encoder = AudioEncoder(owner)
-        self.text_linear_down = nn.Sequential(nn.Linear(hp.encoder_hidden, hp.va_neck_hidden_t), nn.ReLU())
-        self.speaker_linear_p = nn.Sequential(nn.Linear(hp.speaker_embed_dim, hp.va_neck_hidden_p * 2), nn.ReLU())
-        self.speaker_linear = nn.Sequential(nn.Linear(hp.speaker_embed_dim, hp.encoder_hidden), nn.ReLU())
+        self.text_linear_down = KernelMLP(owner, "text_linear_down", (hp.encoder_hidden, hp.va_neck_hidden_t))
+        self.speaker_linear_p = KernelMLP(owner, "speaker_linear_p", (hp.speaker_embed_dim, hp.va_neck_hidden_p * 2))
+        self.speaker_linear = KernelMLP(owner, "speaker_linear", (hp.speaker_embed_dim, hp.encoder_hidden))
 
     def encoder_input_cat(self, mel_target, p_norm, e_input, mel_aug):
         from . import ops
@@ -157,10 +193,6 @@ class LengthRegulator(_Container):          # modules.py:390-423
         return out, mel_len
 
 
-def _mlp(i, h):
-    return nn.Sequential(nn.Linear(i, h), nn.ReLU(), nn.Linear(h, h), nn.ReLU())
-
-
 class _Inspection:
     """Inspection tensor left on StyleModeling by forward() (modules.py:328-331,342-348).  The engine keeps it in the
     activation dtype; callers (synthesize.py:114-144,180-205) feed it to fp32 torch sub-modules, so it is exposed as fp32,
@@ -200,12 +232,12 @@ class StyleModeling(_Container):            # modules.py:238-283
         self.augmentation_classifier_d = AugmentationClassifier(hp.va_neck_hidden_d * 2)
         self.augmentation_classifier_p = AugmentationClassifier(hp.va_neck_hidden_p * 2)
         self.augmentation_classifier_e = AugmentationClassifier(hp.va_neck_hidden_e * 2)
-        self.duration_linear = _mlp(hp.va_neck_hidden_d * 2, H)
-        self.pitch_norm_linear = _mlp(hp.va_neck_hidden_p * 2, H)   # allocated, saved, never used (modules.py:254-257)
-        self.pitch_linear = _mlp(hp.va_neck_hidden_p * 2, H)
-        self.energy_linear = _mlp(hp.va_neck_hidden_e * 2, H)
-        self.residual_linear = _mlp(hp.va_neck_hidden_r * 2, H)
-        self.text_linear_up = nn.Sequential(nn.Linear(hp.va_neck_hidden_t, H), nn.ReLU())
+        self.duration_linear = KernelMLP(owner, "duration_linear", (hp.va_neck_hidden_d * 2, H, H))
+        self.pitch_norm_linear = KernelMLP(owner, "pitch_norm_linear", (hp.va_neck_hidden_p * 2, H, H))   # allocated, saved, never
+        self.pitch_linear = KernelMLP(owner, "pitch_linear", (hp.va_neck_hidden_p * 2, H, H))             # used by forward (modules.py:254-257)
+        self.energy_linear = KernelMLP(owner, "energy_linear", (hp.va_neck_hidden_e * 2, H, H))
+        self.residual_linear = KernelMLP(owner, "residual_linear", (hp.va_neck_hidden_r * 2, H, H))
+        self.text_linear_up = KernelMLP(owner, "text_linear_up", (hp.va_neck_hidden_t, H))
         self.duration_predictor = StylePredictor()
         self.length_regulator = LengthRegulator()
         self.pitch_predictor = StylePredictor()
@@ -238,33 +270,32 @@ class StyleModeling(_Container):            # modules.py:238-283
         from . import ops
         eng = self._owner._engine_for(text_encoding)
         dt = eng.dt
-        parts = [t.to(eng.device, dt) for t in (text_encoding, pitch_encoding, speaker_encoding, energy_encoding, noise_encoding)]
-        enc = torch.cat([p.expand(parts[0].shape[0], parts[0].shape[1], -1) for p in parts], dim=-1).contiguous()
-        src_len = (~src_mask).sum(1).to(eng.device, torch.int64)
-        log_d = eng.predictor(duration_encoding.to(eng.device, dt).contiguous(), src_len, eng.w.pred["duration"])
-        duration = ops.duration_round(log_d, hp.log_offset, float(d_control))
-        tot, _ = ops.length_regulator_scan(duration)
-        T = int(max_len) if max_len else int(tot.max().item())
-        encT, mel_len, _ = ops.length_regulator(enc, duration, T)
-        e_pred = eng.predictor(encT[..., 768:1024], mel_len, eng.w.pred["energy"])
-        p_in = encT[..., 256:512] if speaker_normalized else ops.add(encT[..., 256:512], encT[..., 512:768])
-        p_pred = eng.predictor(p_in, mel_len, eng.w.pred["pitch"])
-        # embeddings as separate outputs like the reference: recover them from sums with zero partners
-        zeros = torch.zeros_like(encT[..., 0:256])
-        w = eng.w
-        both, _, _, _ = ops.bucket_embed_sum(zeros, zeros, None, p_pred, e_pred, float(p_control), float(e_control),
-                                             w.pitch_bins, w.energy_bins, w.pitch_emb, w.energy_emb, want_noisy=False)
-        zero_p = torch.full_like(p_pred, -1e30)   # bucket 0 -> subtract its row to isolate the energy embedding
-        e_only, _, _, _ = ops.bucket_embed_sum(zeros, zeros, None, zero_p, e_pred, 1.0, 1.0, w.pitch_bins, w.energy_bins,
-                                               w.pitch_emb, w.energy_emb, want_noisy=False)
-        e_emb = e_only.float() - w.pitch_emb[0]
-        p_emb = both.float() - e_emb
-        mel_mask = torch.arange(T, device=eng.device).unsqueeze(0) >= mel_len.unsqueeze(1)
-        return (encT[..., 0:256], p_emb.to(dt), encT[..., 512:768], e_emb.to(dt), encT[..., 1024:1280], log_d, p_pred, e_pred,
-                mel_mask)
+        with torch.cuda.device(eng.device):
+            parts = [t.to(eng.device, dt) for t in (text_encoding, pitch_encoding, speaker_encoding, energy_encoding, noise_encoding)]
+            enc = torch.cat([p.expand(parts[0].shape[0], parts[0].shape[1], -1) for p in parts], dim=-1).contiguous()
+            src_len = (~src_mask).sum(1).to(eng.device, torch.int64)
+            log_d = eng.predictor(duration_encoding.to(eng.device, dt).contiguous(), src_len, eng.w.pred["duration"])
+            duration = ops.duration_round(log_d, hp.log_offset, float(d_control))
+            tot, _ = ops.length_regulator_scan(duration)
+            T = int(max_len) if max_len else int(tot.max().item())
+            encT, mel_len, _ = ops.length_regulator(enc, duration, T)
+            e_pred = eng.predictor(encT[..., 768:1024], mel_len, eng.w.pred["energy"])
+            p_in = encT[..., 256:512] if speaker_normalized else ops.add(encT[..., 256:512], encT[..., 512:768])
+            p_pred = eng.predictor(p_in, mel_len, eng.w.pred["pitch"])
+            # one launch: predictions * control (modules.py:299,305), bucketize, and the two embedding rows as separate outputs
+            w = eng.w
+            _, _, _, _, p_scaled, e_scaled, p_emb, e_emb = ops.bucket_embed_sum(
+                None, None, None, p_pred, e_pred, float(p_control), float(e_control), w.pitch_bins, w.energy_bins, w.pitch_emb,
+                w.energy_emb, want_noisy=False, want_scaled=True, want_emb=True, want_sum=False, emb_dtype=dt)
+            mel_mask = torch.arange(T, device=eng.device).unsqueeze(0) >= mel_len.unsqueeze(1)
+        return (encT[..., 0:256], p_emb, encT[..., 512:768], e_emb, encT[..., 1024:1280], log_d, p_scaled, e_scaled, mel_mask)
 
 
 # --------------------------------------------------------------------------------------------- the model
+def _invalidate_after_load(module, incompatible_keys):
+    module._invalidate()
+
+
 class STYLER(nn.Module):
     """Drop-in for the reference `styler.STYLER` (styler.py:13-58), eval-mode forward on B200 kernels.
 
@@ -274,20 +305,40 @@ class STYLER(nn.Module):
 
     def __init__(self, use_postnet=True, precision="bf16"):
         super().__init__()
-        if not use_postnet:
-            raise NotImplementedError("use_postnet=False is not built (every reference caller uses the default)")
         self.precision = precision
         self.style_modeling = StyleModeling(self)
         self.decoder = Decoder()
         self.mel_linear = nn.Linear(hp.decoder_hidden, hp.n_mel_channels)
         self.use_postnet = use_postnet
-        self.postnet = PostNet()
-        self._engine = None
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+        if self.use_postnet:                      # styler.py:24-26: without it decode() returns the mel twice
+            self.postnet = PostNet()
+        # One packed Engine per device.  nn.DataParallel (train.py:33, synthesize.py:62) makes shallow replicas whose
+        # parameters are plain per-device tensors (their `_parameters` is empty, so `replica.state_dict()` has no weights):
+        # the dict and the weak reference below are shared through the copied `__dict__`, so replica i finds (or builds once)
+        # the engine of ITS device, packed from the master's state_dict -- the values the replicas were broadcast.
+        object.__setattr__(self, "_engines", {})
+        object.__setattr__(self, "_master", weakref.ref(self))
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
 
     # -- engine lifecycle ------------------------------------------------------------------------------------
+    def __getstate__(self):                       # copy.deepcopy / torch.save(model): engines and the weak self-reference
+        st = self.__dict__.copy()                 # are per-instance runtime state, rebuilt lazily
+        st.pop("_engines", None)
+        st.pop("_master", None)
+        return st
+
+    def __setstate__(self, st):
+        super().__setstate__(st)
+        object.__setattr__(self, "_engines", {})
+        object.__setattr__(self, "_master", weakref.ref(self))
+
     def _invalidate(self):
-        object.__setattr__(self, "_engine", None)
+        self._engines.clear()
+
+    @property
+    def _engine(self):
+        """The engine of the device the parameters live on (None before the first forward)."""
+        return self._engines.get((self.mel_linear.weight.device, self.precision))
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
@@ -299,32 +350,41 @@ class STYLER(nn.Module):
         return self
 
     def _engine_for(self, like=None):
-        dev = self.mel_linear.weight.device
+        """Engine for the device of `like` (a CUDA tensor handed to a sub-module entry point) or of the parameters."""
+        dev = like.device if torch.is_tensor(like) and like.is_cuda else self.mel_linear.weight.device
         if self.training:
             raise RuntimeError("styler_b200.STYLER implements the eval-mode forward only; call .eval()")
         if dev.type != "cuda":
             raise RuntimeError("styler_b200.STYLER runs only on a CUDA (sm_100a) device; call .cuda() first -- "
                                "there is no CPU fallback")
-        if self._engine is None or self._engine.device != dev or self._engine.precision != self.precision:
-            with torch.no_grad():
-                object.__setattr__(self, "_engine", Engine(self.state_dict(), dev, self.precision))
-        return self._engine
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        key = (dev, self.precision)
+        eng = self._engines.get(key)
+        if eng is None:
+            master = (self._master() or self) if getattr(self, "_is_replica", False) else self
+            with torch.no_grad(), torch.cuda.device(dev):
+                eng = Engine(master.state_dict(), dev, self.precision)
+            self._engines[key] = eng
+        return eng
 
     # -- reference API ----------------------------------------------------------------------------------------
     def decode(self, style_modeling_output, mel_mask):
         """styler.py:29-37: (mel_output, mel_output_postnet), fp32 [B,T,80]."""
-        eng = self._engine_for()
-        x = style_modeling_output.to(eng.device, eng.dt).contiguous()
-        lens = (~mel_mask.to(eng.device)).sum(1).to(torch.int64)
-        return eng.decode(x, lens)
+        eng = self._engine_for(style_modeling_output)
+        with torch.cuda.device(eng.device):
+            x = style_modeling_output.to(eng.device, eng.dt).contiguous()
+            lens = (~mel_mask.to(eng.device)).sum(1).to(torch.int64)
+            return eng.decode(x, lens)
 
     @torch.no_grad()
     def forward(self, src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target=None, p_target=None,
                 e_target=None, max_src_len=None, max_mel_len=None, speaker_embed=None, d_control=1.0, p_control=1.0,
                 e_control=1.0):
         eng = self._engine_for()
-        out = eng.forward(src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target, p_target, e_target,
-                          max_src_len, max_mel_len, speaker_embed, d_control, p_control, e_control)
+        with torch.cuda.device(eng.device):      # kernels, streams and allocations all on the parameters' device
+            out = eng.forward(src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target, p_target, e_target,
+                              max_src_len, max_mel_len, speaker_embed, d_control, p_control, e_control)
         self.style_modeling._store_inspection(eng, out[5], max_mel_len)
         return out
 
@@ -343,6 +403,7 @@ class GraphedSTYLER:
     def __init__(self, model, example_args, example_kwargs, warmup=2):
         self.model = model
         eng = model._engine_for()
+        self._eng = eng          # the graph holds raw pointers into this engine's packed weights / tables / side streams
         dev = eng.device
         if example_kwargs.get("d_target") is None and not example_kwargs.get("max_mel_len"):
             raise ValueError("GraphedSTYLER needs d_target or max_mel_len (no host sync may happen inside a CUDA graph)")
@@ -364,6 +425,14 @@ class GraphedSTYLER:
             self.static_out = model(*self.static_args, **self.static_kwargs)
 
     def __call__(self, *args, **kwargs):
+        if self.model._engine is not self._eng:
+            raise RuntimeError("GraphedSTYLER: the model was moved / reloaded / re-precisioned after capture (its packed "
+                               "weights were released); build a new GraphedSTYLER")
+        for k, v in kwargs.items():
+            if not torch.is_tensor(v) and k in self.static_kwargs and self.static_kwargs[k] != v and \
+                    not (k == "max_mel_len" and v is None):
+                raise ValueError("GraphedSTYLER: %s=%r differs from the captured %r (scalars are baked into the graph)"
+                                 % (k, v, self.static_kwargs[k]))
         for dst, src in zip(self.static_args, args):
             if torch.is_tensor(dst):
                 dst.copy_(src, non_blocking=True)

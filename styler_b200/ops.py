@@ -4,11 +4,37 @@ Tensors are torch CUDA tensors used purely as device buffers; every function enq
 on the current stream and returns its output tensor(s).  Activations are [B, T, C] views whose last stride is 1.
 """
 import ctypes
+import functools
 
 import torch
 
 from . import _lib as L
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, IMPL_AUTO, IMPL_SIMT, IMPL_TC  # noqa: F401
+
+
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first tensor argument current: the library launches on the CURRENT device's
+    stream (`_lib.stream_ptr()`), so a model living on cuda:1 while cuda:0 is current (nn.DataParallel replicas,
+    `model.to('cuda:1')`) must switch first -- otherwise device-1 pointers would be launched on device 0."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a):
+                dev = a.device
+                break
+        if dev is None:
+            for a in kwargs.values():
+                if torch.is_tensor(a):
+                    dev = a.device
+                    break
+        if dev is None or dev.type != "cuda":
+            raise RuntimeError("styler_b200.ops.%s: expected CUDA tensors (the product path has no CPU implementation)" % fn.__name__)
+        if dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _v3(t, name="tensor"):
@@ -19,6 +45,7 @@ def _v3(t, name="tensor"):
     return t, int(t.stride(0)), int(t.stride(1))
 
 
+@_on_tensor_device
 def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=None, residual_f32=None, ln=None, ln_eps=1e-5,
            act2=ACT_NONE, lens=None, dot=None, out=None, want_out=True, out_f32=None, vt=None, vt_col0=0,
            impl=IMPL_AUTO, dilation=1, act_slope=0.0, residual_inv_lrelu=False):
@@ -104,6 +131,7 @@ def make_fft_weights(wqkv, bqkv, wfc, bfc, ln1, w1, b1, w2, b2, ln2, n_head=4, l
     return fw
 
 
+@_on_tensor_device
 def fftblock(x, fw, lens, *, out=None, impl=IMPL_AUTO):
     """One FFT block (styler_fftblock_fwd): x [B,T,d_model] -> y [B,T,d_model]; `out` may be a channel slice of a wider buffer."""
     x, x_bs, x_ld = _v3(x, "x")
@@ -120,6 +148,7 @@ def fftblock(x, fw, lens, *, out=None, impl=IMPL_AUTO):
     return out
 
 
+@_on_tensor_device
 def attention(qk, vt, lens, n_head=4, *, out=None, impl=IMPL_AUTO):
     """ctx[B,T,H*64] = softmax(mask(Q K^T)) V ; qk [B,T,2*H*64] (Q pre-scaled) + vt [B,H*64,Tpad], or the fused
     qkv [B,T,3*H*64] with vt=None (V read row-major)."""
@@ -136,6 +165,7 @@ def attention(qk, vt, lens, n_head=4, *, out=None, impl=IMPL_AUTO):
     return out
 
 
+@_on_tensor_device
 def lrelu_mean(a, b=None, c=None, *, slope_in, slope_out, out=None):
     """out = lrelu(mean_k x_k, slope_out) where the inputs hold y_k = lrelu(x_k, slope_in) (styler_lrelu_mean_fwd)."""
     L.require_cuda(a)
@@ -148,6 +178,7 @@ def lrelu_mean(a, b=None, c=None, *, slope_in, slope_out, out=None):
     return out
 
 
+@_on_tensor_device
 def embed_pos(src_seq, emb, pos, dtype):
     B, Ln = src_seq.shape
     D = emb.shape[1]
@@ -157,6 +188,7 @@ def embed_pos(src_seq, emb, pos, dtype):
     return out
 
 
+@_on_tensor_device
 def add(a, a2=None, rowvec=None, pos=None, out=None):
     """out = (a or 0) (+ a2) (+ rowvec[b] broadcast over t) (+ pos[t] fp32 broadcast over b)."""
     if a is None:
@@ -179,6 +211,7 @@ def add(a, a2=None, rowvec=None, pos=None, out=None):
     return out
 
 
+@_on_tensor_device
 def cast(x, dtype):
     x = x.contiguous()
     out = torch.empty(x.shape, device=x.device, dtype=dtype)
@@ -186,6 +219,7 @@ def cast(x, dtype):
     return out
 
 
+@_on_tensor_device
 def quantize_index(x):
     x = x.contiguous()
     idx = torch.empty(x.shape, device=x.device, dtype=torch.int32)
@@ -193,6 +227,7 @@ def quantize_index(x):
     return idx
 
 
+@_on_tensor_device
 def onehot_conv(idx, wg, bias, dtype):
     """idx int32 [B,T]; wg fp32 [KS, nidx, C]; -> [B,T,C]."""
     B, T = idx.shape
@@ -203,6 +238,7 @@ def onehot_conv(idx, wg, bias, dtype):
     return out
 
 
+@_on_tensor_device
 def groupnorm_relu_(x, gamma, beta, ch_per_group=16, eps=1e-5):
     x3, bs, ld = _v3(x, "x")
     B, T, C = x3.shape
@@ -212,6 +248,7 @@ def groupnorm_relu_(x, gamma, beta, ch_per_group=16, eps=1e-5):
     return x
 
 
+@_on_tensor_device
 def mel_calibrator(x, mel_len, src_len, Lmax, out=None):
     x, x_bs, x_ld = _v3(x, "x")
     B, Tr, C = x.shape
@@ -223,6 +260,7 @@ def mel_calibrator(x, mel_len, src_len, Lmax, out=None):
     return out
 
 
+@_on_tensor_device
 def bilstm_layer(gx, whh, dtype, out=None):
     """gx fp32 [B,L,8H]; whh fp32 [2,4H,H] -> [B,L,2H]."""
     B, Ln, G8 = gx.shape
@@ -236,6 +274,7 @@ def bilstm_layer(gx, whh, dtype, out=None):
     return out
 
 
+@_on_tensor_device
 def classifier_tail(h, w, b):
     h, h_bs, h_ld = _v3(h, "h")
     B, Ln, C = h.shape
@@ -245,6 +284,7 @@ def classifier_tail(h, w, b):
     return out
 
 
+@_on_tensor_device
 def duration_round(log_d, log_offset=1.0, d_control=1.0):
     log_d = log_d.contiguous()
     out = torch.empty_like(log_d)
@@ -253,6 +293,7 @@ def duration_round(log_d, log_offset=1.0, d_control=1.0):
     return out
 
 
+@_on_tensor_device
 def length_regulator(x, duration, Tmax, out=None):
     """x [B,L,C]; duration int64 or float32 [B,L]; -> (out [B,Tmax,C], mel_len int64 [B], cum int32 [B,L])."""
     x, x_bs, x_ld = _v3(x, "x")
@@ -281,28 +322,58 @@ def length_regulator_scan(duration):
     return mel_len, cum
 
 
+@_on_tensor_device
 def bucket_embed_sum(text, spk, noise, p_val, e_val, p_scale, e_scale, pitch_bins, energy_bins, pitch_emb, energy_emb,
-                     want_noisy=True, want_idx=False, out=None, out_noisy=None):
-    text, in_bs, in_ld = _v3(text, "text")
-    spk3, s_bs, s_ld = _v3(spk, "spk")
-    assert (s_bs, s_ld) == (in_bs, in_ld), "text/spk/noise must share strides (slices of one expanded buffer)"
-    B, T, C = text.shape
-    if out is None:
-        out = torch.empty(B, T, C, device=text.device, dtype=text.dtype)
-    out_n = (out_noisy if out_noisy is not None else torch.empty_like(out)) if want_noisy else None
-    assert out.is_contiguous() and (out_n is None or out_n.is_contiguous())
-    p_idx = torch.empty(B, T, device=text.device, dtype=torch.int32) if want_idx else None
-    e_idx = torch.empty(B, T, device=text.device, dtype=torch.int32) if want_idx else None
-    assert p_val.is_contiguous() and e_val.is_contiguous() and p_val.dtype == torch.float32
+                     want_noisy=True, want_idx=False, out=None, out_noisy=None, want_scaled=False, want_emb=False,
+                     want_sum=True, emb_dtype=None):
+    """bucketize + embedding (+ 4-way sum), styler_bucket_embed_sum_fwd.  Inputs are never modified.
+    Returns (out, out_noisy, p_idx, e_idx) and, appended when asked for, (p_scaled, e_scaled) = the predictions times their
+    control factors (fp32) and (pitch_embedding, energy_embedding) = the two embedding rows on their own (dtype of text)."""
+    p_val, e_val = p_val.contiguous(), e_val.contiguous()
+    assert p_val.dtype == torch.float32 and e_val.dtype == torch.float32 and p_val.shape == e_val.shape
+    L.require_cuda(p_val, e_val)
+    B, T = p_val.shape
+    C = pitch_emb.shape[1]
+    dev = p_val.device
+    in_bs = in_ld = 0
+    dt = None
+    if want_sum:
+        text, in_bs, in_ld = _v3(text, "text")
+        spk3, s_bs, s_ld = _v3(spk, "spk")
+        assert (s_bs, s_ld) == (in_bs, in_ld), "text/spk/noise must share strides (slices of one expanded buffer)"
+        assert text.shape == (B, T, C)
+        dt = text.dtype
+        if out is None:
+            out = torch.empty(B, T, C, device=dev, dtype=dt)
+        out_n = (out_noisy if out_noisy is not None else torch.empty_like(out)) if want_noisy else None
+        assert out.is_contiguous() and (out_n is None or out_n.is_contiguous())
+    else:
+        text = spk3 = noise = out = out_n = None
+        want_noisy = False
+    p_idx = torch.empty(B, T, device=dev, dtype=torch.int32) if want_idx else None
+    e_idx = torch.empty(B, T, device=dev, dtype=torch.int32) if want_idx else None
+    p_sc = torch.empty(B, T, device=dev, dtype=torch.float32) if want_scaled else None
+    e_sc = torch.empty(B, T, device=dev, dtype=torch.float32) if want_scaled else None
+    emb_dt = dt if dt is not None else (emb_dtype or torch.float32)
+    p_emb = torch.empty(B, T, C, device=dev, dtype=emb_dt) if want_emb else None
+    e_emb = torch.empty(B, T, C, device=dev, dtype=emb_dt) if want_emb else None
     L.check(L.lib().styler_bucket_embed_sum_fwd(L.ptr(text), L.ptr(spk3), L.ptr(noise) if want_noisy else None, in_bs,
                                                 in_ld, L.ptr(p_val), L.ptr(e_val), p_scale, e_scale, L.ptr(pitch_bins),
                                                 L.ptr(energy_bins), pitch_bins.numel(), L.ptr(pitch_emb),
-                                                L.ptr(energy_emb), L.ptr(out), L.ptr(out_n), int(out.stride(0)),
-                                                int(out.stride(1)), L.ptr(p_idx), L.ptr(e_idx), B, T, C,
-                                                L.dtype_code(text.dtype), L.stream_ptr()), "bucket_embed_sum")
-    return out, out_n, p_idx, e_idx
+                                                L.ptr(energy_emb), L.ptr(out), L.ptr(out_n),
+                                                int(out.stride(0)) if out is not None else 0,
+                                                int(out.stride(1)) if out is not None else 0, L.ptr(p_idx), L.ptr(e_idx),
+                                                L.ptr(p_sc), L.ptr(e_sc), L.ptr(p_emb), L.ptr(e_emb), B, T, C,
+                                                L.dtype_code(emb_dt), L.stream_ptr()), "bucket_embed_sum")
+    res = (out, out_n, p_idx, e_idx)
+    if want_scaled:
+        res = res + (p_sc, e_sc)
+    if want_emb:
+        res = res + (p_emb, e_emb)
+    return res
 
 
+@_on_tensor_device
 def stft_mel(y, mel_basis):
     """y fp32 [B,N] -> (mel fp32 [B,n_mels,F], energy fp32 [B,F])."""
     y = y.contiguous()
@@ -317,8 +388,11 @@ def stft_mel(y, mel_basis):
     return mel, energy
 
 
-def stft_mel_ex(y, mel_basis, *, in_scale=1.0, clamp=False, frame_major=False, energy_range=None):
-    """Fused front end (styler_stft_mel_ex_fwd): returns (mel, energy, clip_flag int32 [B] or None, e_input or None)."""
+@_on_tensor_device
+def stft_mel_ex(y, mel_basis, *, in_scale=1.0, clamp=False, frame_major=False, energy_range=None, n_samples=None):
+    """Fused front end (styler_stft_mel_ex_fwd): returns (mel, energy, clip_flag int32 [B] or None, e_input or None).
+    n_samples (int64 [B], device): true length of every zero-padded row -- each utterance is reflected around its own end
+    and frames beyond 1 + n_samples[b] // 256 come back as zeros."""
     y = y.contiguous()
     B, N = y.shape
     n_mels = mel_basis.shape[0]
@@ -329,12 +403,16 @@ def stft_mel_ex(y, mel_basis, *, in_scale=1.0, clamp=False, frame_major=False, e
     flag = torch.empty(B, device=y.device, dtype=torch.int32) if clamp else None
     e_in = torch.empty(B, F, device=y.device, dtype=torch.float32) if energy_range is not None else None
     e_min, e_max = (float(energy_range[0]), float(energy_range[1])) if energy_range is not None else (0.0, 1.0)
+    if n_samples is not None:
+        assert n_samples.dtype == torch.int64 and n_samples.is_cuda and n_samples.numel() == B
+        n_samples = n_samples.contiguous()
     L.check(L.lib().styler_stft_mel_ex_fwd(L.ptr(y), B, N, L.ptr(mel_basis), n_mels, L.ptr(band), L.ptr(mel), L.ptr(energy),
                                            float(in_scale), 1 if clamp else 0, L.ptr(flag), 1 if frame_major else 0,
-                                           L.ptr(e_in), e_min, e_max, L.stream_ptr()), "stft_mel_ex")
+                                           L.ptr(e_in), e_min, e_max, L.ptr(n_samples), L.stream_ptr()), "stft_mel_ex")
     return mel, energy, flag, e_in
 
 
+@_on_tensor_device
 def f0_norm(f0, lens=None):
     """f0_normalization (utils.py:387-409) over a padded [B,T] fp32 batch of log-f0 contours."""
     f0 = f0.contiguous()

@@ -329,12 +329,34 @@ def test_classifier_tail_duration(cuda):
     ref = F.log_softmax(F.linear(h, w, b), -1).mean(1)
     got = ops.classifier_tail(h.to(cuda), w.to(cuda), b.to(cuda)).cpu()
     assert torch.allclose(got, ref, atol=1e-5)
-    log_d = torch.randn(4, 33, generator=g) * 1.5
-    for ctl in (1.0, 1.3):
+
+
+def test_duration_round_exact(cuda):
+    """modules.py:357-358 is an fp -> int boundary: clamp(round(exp(log_d) - log_offset) * d_control, min=0) must be EQUAL to
+    the reference arithmetic, not close.  expf on the device and torch.exp on the host may differ in the last ulp, which only
+    matters within an ulp of a .5 tie: (1) inputs are drawn with exp(log_d) at least 1e-3 away from every tie -> require
+    equality on all of them; (2) the tie rule itself (half to even, torch.round) is pinned with exactly representable ties."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    log_d = torch.randn(64, 257, generator=g) * 1.5
+    frac = (torch.exp(log_d.double()) - 1.0) % 1.0
+    keep = (frac - 0.5).abs() > 1e-3
+    log_d = torch.where(keep, log_d, torch.zeros_like(log_d))            # exp(0) - 1 = 0: far from a tie
+    assert keep.float().mean() > 0.99
+    for ctl in (1.0, 1.3, 0.5):
         got = ops.duration_round(log_d.to(cuda), 1.0, ctl).cpu()
         ref = so.duration_from_log(log_d, ctl)
-        assert (got != ref).float().mean() < 0.01           # exp() may differ by 1 ulp exactly at a .5 tie
-        assert (got - ref).abs().max() <= ctl + 1e-6
+        assert torch.equal(got, ref), (ctl, (got != ref).sum().item())
+        assert (got >= 0).all()
+    # exact ties: exp(0) == 1 exactly, so rint(1 - off) sees k + 0.5 with no rounding error; half-to-even, then * d_control
+    zeros = torch.zeros(1, 8, device=cuda)
+    for off, want in ((0.5, 0.0), (-0.5, 2.0), (-1.5, 2.0), (-2.5, 4.0), (-3.5, 4.0), (1.5, 0.0), (2.5, 0.0)):
+        got = ops.duration_round(zeros, off, 1.0).cpu()
+        assert (got == want).all(), (off, got[0, 0].item(), want)
+        assert (got == torch.clamp(torch.round(torch.tensor(1.0 - off)), min=0)).all()
+    assert (ops.duration_round(zeros, -1.5, 1.5).cpu() == 3.0).all()      # round BEFORE scaling by d_control (2 * 1.5)
+    # very negative predictions clamp at zero; the LengthRegulator then truncates toward zero (int(x.item()))
+    assert (ops.duration_round(torch.full((1, 4), -30.0, device=cuda), 1.0, 1.7).cpu() == 0).all()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
@@ -381,6 +403,20 @@ def test_bucket_embed_sum(cuda):
     assert torch.equal(gpi.cpu().long(), pi) and torch.equal(gei.cpu().long(), ei)
     assert torch.equal(out.cpu(), ref)
     assert torch.allclose(out_n.cpu(), ref + noise, atol=1e-6)
+    # control factors (modules.py:370,380): scaled predictions come back as separate outputs, the inputs stay untouched, and
+    # the embedding rows on their own (predict_inference, modules.py:299-309) are exact copies of the table rows
+    pd, ed = p.to(cuda), e.to(cuda)
+    res = ops.bucket_embed_sum(None, None, None, pd, ed, 1.3, 0.7, sd[P + "pitch_bins"].to(cuda), sd[P + "energy_bins"].to(cuda),
+                               sd[P + "pitch_embedding.weight"].to(cuda), sd[P + "energy_embedding.weight"].to(cuda),
+                               want_idx=True, want_scaled=True, want_emb=True, want_sum=False)
+    _, _, gpi, gei, psc, esc, pemb, eemb = res
+    assert torch.equal(pd.cpu(), p) and torch.equal(ed.cpu(), e), "inputs must not be modified"
+    ps, es = p * 1.3, e * 0.7
+    assert torch.equal(psc.cpu(), ps) and torch.equal(esc.cpu(), es)
+    pi2, ei2 = torch.bucketize(ps, sd[P + "pitch_bins"]), torch.bucketize(es, sd[P + "energy_bins"])
+    assert torch.equal(gpi.cpu().long(), pi2) and torch.equal(gei.cpu().long(), ei2)
+    assert torch.equal(pemb.cpu(), F.embedding(pi2, sd[P + "pitch_embedding.weight"]))
+    assert torch.equal(eemb.cpu(), F.embedding(ei2, sd[P + "energy_embedding.weight"]))
 
 
 def test_stft_mel(cuda):
