@@ -41,12 +41,30 @@ NBUF = 4
 
 
 def load_peaks():
+    """MEASURED_PEAKS.json (driver-written): cuBLAS bf16 burst and sustained TFLOP/s, STREAM-copy GB/s; else the
+    profiling recipe's fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, ~1.4 sustained, 6.65 TB/s)."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return dict(tensor=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured")
+        return dict(burst=float(p["bf16_tflops"]), sustained=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]),
+                    sm_max_mhz=float(p.get("sm_max_mhz", 1965.0)), src="measured")
     except Exception:
-        return dict(tensor=1400.0, hbm=6650.0, src="fallback")
+        return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, sm_max_mhz=1965.0, src="fallback")
+
+
+def tensor_roofline(ach_tflops, peaks, clocks, scale=1.0):
+    """Fractions of BOTH cuBLAS peaks; `frac`/`peak` is the one that matches the SM clock sampled during the timed region:
+    the burst figure when the median clock stayed within 10 % of the maximum (a short run that never settles under the
+    power cap), the sustained figure when the clock had dropped (a long, thermally settled step).  scale: 0.5 for tf32."""
+    burst, sust = peaks["burst"] * scale, peaks["sustained"] * scale
+    mhz = (clocks or {}).get("sm_mhz")
+    mx = (clocks or {}).get("sm_max_mhz") or peaks["sm_max_mhz"]
+    use_burst = mhz is None or mhz >= 0.9 * mx
+    peak = burst if use_burst else sust
+    return {"peak": peak, "frac": ach_tflops / peak, "frac_burst": ach_tflops / burst, "frac_sustained": ach_tflops / sust,
+            "peak_source": "%s %s (median SM clock %s MHz of %s during the timed region)" % (
+                peaks["src"], "bf16_tflops (burst)" if use_burst else "bf16_tflops_sustained", mhz, mx) +
+            ("" if scale == 1.0 else " x %.1f (tf32)" % scale)}
 
 
 class ClockSampler:
@@ -221,7 +239,7 @@ def run_vocoder(args):
     launches = _lib.launch_count() - n0
     fl = vocoder_flops_per_utt(T, CONFIG_V1) * B
     peaks = load_peaks()
-    peak = peaks["tensor"] if args.precision == "bf16" else peaks["tensor"] / 2
+    roofv = tensor_roofline(fl / (ms * 1e-3) / 1e12, peaks, None, 1.0 if args.precision == "bf16" else 0.5)
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import hifigan_oracle as ho          # CPU-baseline leg only
@@ -246,11 +264,194 @@ def run_vocoder(args):
                                "seeded synthetic weights" % (B, T, T * 256), "global_batch": B,
                    "l2": "per-step activations (134 MB per 32-channel tensor) >> L2"},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "whole forward (72 resblock convs + 4 transposed convs)", "achieved": fl / (ms * 1e-3) / 1e12,
-                     "peak": peak, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak,
-                     "peak_source": peaks["src"] + " bf16_tflops_sustained" + ("" if args.precision == "bf16" else " / 2 (tf32)"),
-                     "flops_per_launch": fl, "traffic": None},
+        "roofline": dict({"bound": "tensor", "kernel": "whole forward (72 resblock convs + 4 transposed convs)",
+                          "achieved": fl / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "flops_per_launch": fl, "traffic": None}, **roofv),
         "realtime_factor_22050Hz": wav.numel() / (ms * 1e-3) / 22050.0, "cpu_baseline": cpu}))
+
+
+def _flush_buffer(dev):
+    return torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > the 126 MB L2
+
+
+def run_fftblock(args):
+    """BASELINE configs[1]: ONE FFTBlock (attention + Conv1d FFN, transformer/Layers.py:26-34) at B=16, L=128, fp32 I/O --
+    the fp32-parity tensor-core mode (tcgen05 kind::tf32, fp32 storage) unless --precision bf16.  tokens/s; L2 flushed
+    between timed iterations (the whole problem, 2 MB of activations + 5 MB of weights, would otherwise sit in L2)."""
+    from styler_b200 import _lib
+    from styler_b200 import synthetic as syn
+    from styler_b200.engine import Engine
+    precision = args.precision if args.precision_given else "tf32"
+    B, Ln = 16, 128
+    dev = torch.device("cuda", 0)
+    sd = syn.make_state_dict(2)
+    eng = Engine(sd, dev, precision)
+    W = eng.w.dec_layers[2]
+    g = torch.Generator().manual_seed(9)
+    x_host = torch.randn(B, Ln, 256, generator=g).pin_memory()
+    lens = torch.randint(64, Ln + 1, (B,), generator=g)
+    lens[0] = Ln
+    x_host.masked_fill_(syn.mask_from_lengths(lens, Ln).unsqueeze(-1), 0)
+    lens_d = lens.to(dev)
+    x_dev = x_host.to(dev).to(eng.dt)
+    out = torch.empty(B, Ln, 256, device=dev, dtype=eng.dt)
+    flush = _flush_buffer(dev)
+    steps, warm = args.steps, max(args.warmup, 3)
+    for _ in range(warm):
+        eng.fft_block(x_dev, lens_d, W, out=out)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.__enter__()
+    time.sleep(0.3)
+    clocks.mark()
+    n0 = _lib.launch_count()
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.fft_block(x_dev, lens_d, W, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    ms = tot / steps
+    # end to end: fp32 host buffer -> H2D -> (cast) -> block -> (cast) -> D2H of the fp32 result
+    y_host = torch.empty(B, Ln, 256, dtype=torch.float32).pin_memory()
+
+    def e2e_once():
+        xd = x_host.to(dev, non_blocking=True)
+        y = eng.fft_block(eng._act(xd), lens_d, W)
+        y_host.copy_(y if y.dtype == torch.float32 else y.float(), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        e2e_once()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_once()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    clocks.__exit__()
+    flops = (5898240.0) * B * Ln                  # SURVEY.md 8(d): 5,767,168 + 1024*L per token at L=128 -> 12.08 GFLOP
+    peaks = load_peaks()
+    ck = clocks.summary()
+    ach = flops / (ms * 1e-3) / 1e12
+    roof = dict({"bound": "tensor", "kernel": "one FFT block = 5 launches (QKV, attention, out-proj+LN, Conv1d k9+ReLU, Conv1d k1+LN)",
+                 "achieved": ach, "unit": "TFLOP/s", "flops_per_launch": flops, "traffic": None,
+                 "note": "2048 tokens = 16 M-tiles of 128: far too small to fill 148 SMs; launch latency and tile quantisation bound it"},
+                **tensor_roofline(ach, peaks, ck, 0.5 if precision == "tf32" else 1.0))
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import styler_oracle as so       # CPU-baseline leg only
+        torch.set_num_threads(host_threads())
+        xm, mask = x_host.clone(), so.mask_from_lengths(lens, Ln)
+        with torch.no_grad():
+            so.fft_block(sd, "decoder.layer_stack.2.", xm, mask)
+            t0 = time.perf_counter()
+            reps = 20
+            for _ in range(reps):
+                so.fft_block(sd, "decoder.layer_stack.2.", xm, mask)
+            dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": B * Ln / dt, "unit": "tokens/s", "cores": host_threads(), "kind": "port",
+               "sample": "oracle port (torch CPU fp32) of the same FFT block call, mean of %d (%.1f ms each)" % (reps, dt * 1e3)}
+    print(json.dumps({
+        "metric": "tokens/sec (one FFTBlock: attention + Conv1d FFN)", "value": B * Ln / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32" if precision == "tf32" else precision, "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: one FFTBlock(256, 1024, 4 heads), B=%d, L=%d, ragged key mask, fp32 I/O, %s compute"
+                               % (B, Ln, precision), "global_batch": B, "l2": "256 MB flush write between timed iterations"},
+        "e2e": {"value": B * Ln / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": e2e_ms},
+        "gpu_launches": launches, "clocks": ck, "roofline": roof, "cpu_baseline": cpu}))
+
+
+def run_stft(args):
+    """BASELINE configs[3]: TacotronSTFT mel extraction, B=256 x 22050 Hz x 4 s, 1024-pt FFT, hop 256, 80 mels -> STFT frames/s."""
+    from styler_b200 import TacotronSTFT, _lib
+    B, N = 256, 88200
+    F = 1 + N // 256
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(5)
+    y_host = ((torch.rand(B, N, generator=g) * 2 - 1) * 0.5).pin_memory()
+    ys = [y_host.to(dev), (y_host * 0.5).to(dev)]              # 2 x 90 MB inputs; L2 flushed anyway
+    stft = TacotronSTFT().to(dev)
+    flush = _flush_buffer(dev)
+    steps, warm = args.steps, max(args.warmup, 3)
+    for i in range(warm):
+        stft.mel_spectrogram(ys[i % 2])
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.__enter__()
+    time.sleep(0.3)
+    clocks.mark()
+    n0 = _lib.launch_count()
+    tot = 0.0
+    for i in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mel, energy = stft.mel_spectrogram(ys[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    ms = tot / steps
+    mel_host = torch.empty(B, 80, F, dtype=torch.float32).pin_memory()
+    en_host = torch.empty(B, F, dtype=torch.float32).pin_memory()
+
+    def e2e_once():
+        yd = y_host.to(dev, non_blocking=True)
+        m, e = stft.mel_spectrogram(yd)
+        mel_host.copy_(m, non_blocking=True)
+        en_host.copy_(e, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        e2e_once()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_once()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    clocks.__exit__()
+    peaks = load_peaks()
+    nbytes = B * (N * 4 + F * 80 * 4 + F * 4)      # SURVEY.md 8(d): 464,580 B per utterance -> 118.9 MB
+    ach = nbytes / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "stft_kernel.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "stft_mel_kernel (reflect pad + Hann + 1024-pt real FFT + magnitude + mel + log + energy, one launch)",
+            "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "peak_source": peaks["src"] + " hbm_gbs",
+            "bytes_per_launch": nbytes, "traffic": traffic,
+            "note": "HBM is the contractual bound (SURVEY.md 8(d)); the FFT stage is ALU/issue work, see profiles/"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import stft_oracle               # CPU-baseline leg only
+        torch.set_num_threads(host_threads())
+        cb = 32
+        yc = y_host[:cb].clone()
+        with torch.no_grad():
+            stft_oracle.mel_spectrogram(yc, dense=True)
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                stft_oracle.mel_spectrogram(yc, dense=True)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+        cpu = {"value": cb * F / best, "unit": "STFT frames/s", "cores": host_threads(), "kind": "port",
+               "sample": "oracle port of the reference's dense conv-DFT path (audio/stft.py:51-79), B=%d of the same 4 s utterances, "
+                         "best of 3 (%.2f s each)" % (cb, best)}
+    print(json.dumps({
+        "metric": "STFT frames/sec (TacotronSTFT mel extraction)", "value": B * F / (ms * 1e-3), "unit": "STFT frames/s", "n_gpus": 1,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: TacotronSTFT mel extraction, B=%d x 22050 Hz x 4 s (%d samples), n_fft=1024, hop=256, "
+                               "80 mels -> %d frames each" % (B, N, F), "global_batch": B, "l2": "256 MB flush write between timed iterations"},
+        "utterances_per_s": B / (ms * 1e-3),
+        "e2e": {"value": B * F / (e2e_ms * 1e-3), "unit": "STFT frames/s", "h2d_bytes_per_step": y_host.numel() * 4,
+                "d2h_bytes_per_step": (mel_host.numel() + en_host.numel()) * 4, "ms_per_step": e2e_ms},
+        "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu}))
 
 
 def main():
@@ -259,15 +460,25 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the forward as one CUDA graph per resident batch (experiment)")
-    ap.add_argument("--workload", default="styler", choices=["styler", "vocoder"],
-                    help="styler = BASELINE.json's headline metric (default); vocoder = secondary HiFi-GAN line (single GPU)")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every forward kernel by kernel instead of replaying CUDA graphs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the tf32 and B=1 latency side measurements")
+    ap.add_argument("--workload", default="styler", choices=["styler", "vocoder", "fftblock", "stft"],
+                    help="styler = BASELINE.json's headline metric, configs[2] (default); fftblock = configs[1]; stft = configs[3]; "
+                         "vocoder = secondary HiFi-GAN line (all but styler: single GPU)")
     args = ap.parse_args()
+    args.precision_given = args.precision is not None
+    args.precision = args.precision or "bf16"
     if args.workload == "vocoder":
         args.steps = min(args.steps, 10)
         run_vocoder(args)
+        return
+    if args.workload == "fftblock":
+        run_fftblock(args)
+        return
+    if args.workload == "stft":
+        run_stft(args)
         return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -279,7 +490,7 @@ def main():
 
     import torch.distributed as dist
     from styler_b200 import synthetic as so      # seeded synthetic weights/inputs (no oracle import on the GPU arm)
-    from styler_b200 import STYLER, _lib
+    from styler_b200 import STYLER, GraphedSTYLER, _lib
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     model = STYLER(precision=args.precision)
@@ -296,19 +507,38 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     frames_per_step = int(host[0]["mel_len"].sum().item())
 
-    gatherer = sdist.AsyncGather(dev) if world > 1 else None
-    graphs = {}
-
-    def step(bt):
+    def split(bt):
         a = (bt["src_seq"], bt["mel_target"], bt["mel_aug"], bt["p_norm"], bt["e_input"], bt["src_len"], bt["mel_len"])
         kw = dict(d_target=bt["d_target"], p_target=bt["p_target"], e_target=bt["e_target"], max_src_len=L, max_mel_len=T,
                   speaker_embed=bt["speaker_embed"])
-        if args.graph and id(bt) in graphs:
-            out = graphs[id(bt)](*a, **kw)
+        return a, kw
+
+    # Fixed geometry -> the forward is replayed as a CUDA graph (GraphedSTYLER: ~130 launches + the side-stream fork/join of
+    # the audio-encoder branches become one graph launch).  TWO graphs with their own static input/output buffers alternate,
+    # so the gather (N > 1) or the D2H copies (e2e) of step i can still be reading graph k's outputs while step i+1 runs in
+    # the other graph.
+    use_graph = not args.no_graph
+    gatherer = sdist.AsyncGather(dev) if world > 1 else None
+    for i in range(args.warmup):                    # eager warm-up: engine build, position tables, allocator pools
+        model(*split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
+    torch.cuda.synchronize()
+    graphs = []
+    if use_graph:
+        a0, k0 = split(resident[0])
+        graphs = [GraphedSTYLER(model, a0, k0, warmup=1) for _ in range(2)]
+
+    def step(bt, slot):
+        a, kw = split(bt)
+        if use_graph:
+            if gatherer is not None:
+                gatherer.before_reuse(slot)          # the previous gather out of this graph's static outputs has drained
+            out = graphs[slot](*a, **kw)
+            packed = graphs[slot].packed
         else:
             out = model(*a, **kw)
-        if gatherer is not None:   # NCCL gather of the 4 mels + lengths to rank 0 on the comm stream (overlaps the next step)
-            gatherer.launch([out[0][0], out[0][1], out[1][0], out[1][1], out[7]])
+            packed = model._engine.last_packed
+        if gatherer is not None:   # ONE NCCL gather (4 mels + lengths, one byte buffer) to rank 0 on the comm stream
+            gatherer.launch_packed(packed, slot)
         return out
 
     def barrier():
@@ -329,6 +559,8 @@ def main():
             fn(i)
             if i == min(3, steps) - 1:               # host time per step while the launch queue is still empty: later steps
                 enqueue[0] = (time.perf_counter() - t0) / (i + 1)   # are throttled by queue back-pressure to the device pace
+        if gatherer is not None:
+            gatherer.wait()                          # the timed events cover the gathers: join the comm stream before e1
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -341,42 +573,44 @@ def main():
     clocks = ClockSampler(local)
     clocks.__enter__()
     for i in range(args.warmup):
-        step(resident[i % NBUF])
+        step(resident[i % NBUF], i % 2)
     torch.cuda.synchronize()
     t_w = time.perf_counter()
     while not clocks.rows and clocks.proc is not None and time.perf_counter() - t_w < 3.0:
         time.sleep(0.05)                              # first sample seen: the sampler is up
-    if args.graph:
-        from styler_b200 import GraphedSTYLER
-        g0 = GraphedSTYLER(model, (resident[0]["src_seq"], resident[0]["mel_target"], resident[0]["mel_aug"], resident[0]["p_norm"],
-                                   resident[0]["e_input"], resident[0]["src_len"], resident[0]["mel_len"]),
-                           dict(d_target=resident[0]["d_target"], p_target=resident[0]["p_target"], e_target=resident[0]["e_target"],
-                                max_src_len=L, max_mel_len=T, speaker_embed=resident[0]["speaker_embed"]))
-        for bt in resident:
-            graphs[id(bt)] = g0          # one graph; inputs are copied into its static buffers on every replay
 
     # ---- device-resident timed region (value) + per-launch events on the dominant kernel ----------------------
-    # per-launch CUDA events around the dominant kernel (FFN Conv1d k9) are recorded inside the native FFT-block call
-    _lib.check(_lib.lib().styler_debug_ffn1_timing(1, T), "ffn1_timing")
     launches0 = _lib.launch_count()
     clocks.mark()
-    secs, wall = timed(lambda i: step(resident[i % NBUF]), args.steps)
+    secs, wall = timed(lambda i: step(resident[i % NBUF], i % 2), args.steps)
     clocks.__exit__()
-    launches = _lib.launch_count() - launches0
+    launches_counted = _lib.launch_count() - launches0
+    value = world * frames_per_step * args.steps / secs
+    ck = clocks.summary()
+
+    # Roofline leg: the dominant kernel (FFN Conv1d k9) timed live with CUDA events around each of its launches, recorded
+    # inside the native FFT-block call while the same forward runs eagerly (events cannot be read back out of a graph
+    # replay) -- same kernels, same shapes, same clocks; `launches_per_step` is counted in this pass too.
     import ctypes
+    roof_steps = min(args.steps, 10)
+    _lib.check(_lib.lib().styler_debug_ffn1_timing(1, T), "ffn1_timing")
+    n0 = _lib.launch_count()
+    for i in range(roof_steps):
+        model(*split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
+    torch.cuda.synchronize()
+    launches_per_step = (_lib.launch_count() - n0) // max(roof_steps, 1)
     t_ms, t_n, t_b, t_t = ctypes.c_float(0), ctypes.c_int32(0), ctypes.c_int64(0), ctypes.c_int64(0)
     _lib.check(_lib.lib().styler_debug_ffn1_timing_read(ctypes.byref(t_ms), ctypes.byref(t_n), ctypes.byref(t_b), ctypes.byref(t_t)),
                "ffn1_timing_read")
     _lib.check(_lib.lib().styler_debug_ffn1_timing(0, 0), "ffn1_timing")
     torch.cuda.synchronize()
-    value = world * frames_per_step * args.steps / secs
+    launches = launches_per_step * args.steps if use_graph else launches_counted
 
-    dec = [(t_ms.value / t_n.value, int(t_b.value), int(t_t.value))] * int(t_n.value) if t_n.value > 0 else []   # decoder-level launches (T >= 1024)
     peaks = load_peaks()
     roof = None
-    if dec:
-        avg_ms = sum(d[0] for d in dec) / len(dec)
-        flops = 2.0 * dec[0][1] * dec[0][2] * 1024 * 9 * 256
+    if t_n.value > 0:
+        avg_ms = t_ms.value / t_n.value
+        flops = 2.0 * int(t_b.value) * int(t_t.value) * 1024 * 9 * 256
         ach = flops / (avg_ms * 1e-3) / 1e12
         traffic = None
         try:
@@ -384,28 +618,32 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "conv1d_tc_kernel<bf16> FFN Conv1d k=9 256->1024 (+bias+ReLU)",
-                "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
-                "peak_source": peaks["src"] + " bf16_tflops_sustained", "avg_launch_ms": avg_ms, "launches_timed": len(dec),
-                "flops_per_launch": flops, "traffic": traffic}
+        roof = dict({"bound": "tensor", "kernel": "conv1d_tc_kernel<bf16> FFN Conv1d k=9 256->1024 (+bias+ReLU), B=%d T=%d" % (t_b.value, t_t.value),
+                     "achieved": ach, "unit": "TFLOP/s", "avg_launch_ms": avg_ms, "launches_timed": int(t_n.value),
+                     "flops_per_launch": flops, "traffic": traffic},
+                    **tensor_roofline(ach, peaks, ck, 1.0 if args.precision == "bf16" else 0.5))
+        roof["whole_step"] = {"flops": 5.53e12 * B_PER_GPU / 64, "achieved": 5.53e12 * B_PER_GPU / 64 / (secs / args.steps) / 1e12,
+                              "unit": "TFLOP/s", "note": "SURVEY.md 8(d): 86.35 GFLOP per utterance x 64; step time from `value`"}
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------
-    # Two user streams alternate (each with its own pinned result buffers): step i's H2D / D2H copies overlap step
-    # i+-1's kernels, as a serving loop would drive the public API.  Every step still does its own H2D of all inputs and
-    # D2H of its results inside the timed region.
+    # Two user streams alternate (each with its own graph / pinned result buffers): step i's H2D / D2H copies overlap step
+    # i+-1's kernels, as a serving loop would drive the public API.  Every step does its own H2D of all inputs and the D2H of
+    # ALL FOUR mel tensors + lengths (one packed buffer) inside the timed region.
+    from styler_b200.engine import packed_nbytes
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    d2h = [[torch.empty(B_PER_GPU, T, 80, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
-    len_buf = [torch.empty(B_PER_GPU, dtype=torch.int64).pin_memory() for _ in range(2)]
+    d2h = [torch.empty(packed_nbytes(B_PER_GPU, T), dtype=torch.uint8).pin_memory() for _ in range(2)]
 
     def e2e_step(i):
         k = i % 2
         with torch.cuda.stream(e2e_streams[k]):
             hb = host[i % NBUF]
-            bt = {kk: v.to(dev, non_blocking=True) for kk, v in hb.items()}
-            out = step(bt)
-            d2h[k][0].copy_(out[1][0], non_blocking=True)
-            d2h[k][1].copy_(out[1][1], non_blocking=True)
-            len_buf[k].copy_(out[7], non_blocking=True)
+            if use_graph:                              # GraphedSTYLER copies the (pinned host) inputs straight into its static buffers
+                step(hb, k)
+                d2h[k].copy_(graphs[k].packed, non_blocking=True)
+            else:
+                bt = {kk: v.to(dev, non_blocking=True) for kk, v in hb.items()}
+                step(bt, k)
+                d2h[k].copy_(model._engine.last_packed, non_blocking=True)
 
     def e2e_timed(steps):
         barrier()
@@ -427,7 +665,60 @@ def main():
         e2e_step(i)                                 # channels and receive buffers of the e2e streams exist before timing
     e2e_secs = e2e_timed(args.steps)
     e2e_value = world * frames_per_step * args.steps / e2e_secs
-    d2h_bytes = 2 * d2h[0][0].numel() * 4 + len_buf[0].numel() * 8
+    d2h_bytes = d2h[0].numel()
+
+    # ---- side measurements (rank 0, N = 1): the fp32-parity tf32 mode on the same workload, and BASELINE configs[0] latency ----
+    extras = {}
+    if world == 1 and not args.no_extras:
+        torch.cuda.synchronize()
+        del graphs[:]
+        other = "tf32" if args.precision == "bf16" else "bf16"
+        m2 = STYLER(precision=other)
+        m2.load_state_dict(so.make_state_dict(0))
+        m2 = m2.to(dev).eval()
+        a0, k0 = split(resident[0])
+        for _ in range(3):
+            m2(*a0, **k0)
+        torch.cuda.synchronize()
+        n2 = min(args.steps, 10)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n2):
+            a, kw = split(resident[i % NBUF])
+            m2(*a, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / n2
+        extras[other + "_same_workload"] = {"ms_per_step": ms2, "value": frames_per_step / (ms2 * 1e-3), "unit": "mel-frames/s",
+                                            "steps": n2, "note": "device-resident, eager launches; tf32 = fp32 storage + tcgen05 kind::tf32, "
+                                                                 "the mode that meets the 1e-3 fp32 tolerance"}
+        del m2
+        # BASELINE configs[0]: single utterance, 50 phonemes, free-running durations (8 frames/phoneme via the duration bias)
+        sd1 = so.set_duration_bias(so.make_state_dict(0), FRAMES)
+        m1 = STYLER(precision=args.precision)
+        m1.load_state_dict(sd1)
+        m1 = m1.to(dev).eval()
+        b1 = so.make_inputs(B=1, L=50, Tr=400, seed=16, d_mode=None)
+        a1 = tuple(b1[k].to(dev) for k in ("src_seq", "mel_target", "mel_aug", "p_norm", "e_input", "src_len", "mel_len"))
+        k1 = dict(max_src_len=50, speaker_embed=b1["speaker_embed"].to(dev))
+
+        def lat(fn, n=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+                torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / n * 1e3
+
+        eager_ms = lat(lambda: m1(*a1, **k1))
+        g1 = GraphedSTYLER(m1, a1, dict(k1, max_mel_len=50 * FRAMES))
+        graph_ms = lat(lambda: g1(*a1, **k1))
+        extras["latency_config0_b1_l50"] = {"eager_ms": eager_ms, "graph_ms": graph_ms, "mel_frames": 50 * FRAMES,
+                                            "note": "BASELINE configs[0] on the GPU: one utterance, 50 phonemes -> 400 frames, free-running; "
+                                                    "wall clock per call incl. synchronize; eager has one host read of max(mel_len)"}
+        del g1, m1
 
     if rank != 0:
         if world > 1:
@@ -448,11 +739,15 @@ def main():
                                "(teacher-forced %d frames/phoneme), ref mel %d frames, 80-bin, %s compute; random-init weights"
                                % (B_PER_GPU, L, T, FRAMES, T, args.precision),
                    "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world,
+                   "launch": "CUDA-graph replay of the forward (2 alternating graphs)" if use_graph else "eager kernel launches",
+                   "gather": "one packed NCCL gather per step (4 fp32 mels + lengths, %d bytes/rank), inside the timed events"
+                             % packed_nbytes(B_PER_GPU, T) if world > 1 else "none (N=1)",
                    "l2": "inputs rotate over %d resident batches (> L2); per-step activations >> L2; no explicit flush" % NBUF},
         "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_secs / args.steps},
-        "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
-        "wall_s_timed_region": wall, "host_enqueue_ms_per_step": 1e3 * enqueue[0]}))
+                "ms_per_step": 1e3 * e2e_secs / args.steps,
+                "what": "pinned host inputs -> H2D -> forward -> D2H of all four mel tensors + lengths, every step"},
+        "gpu_launches": launches, "launches_per_step": launches_per_step, "clocks": ck, "roofline": roof, "cpu_baseline": cpu,
+        "wall_s_timed_region": wall, "host_enqueue_ms_per_step": 1e3 * enqueue[0], "extras": extras or None}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

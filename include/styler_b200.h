@@ -203,6 +203,12 @@ int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, const float* me
  * (unvoiced frames marked <= -1e10 keep their value; rows with undefined statistics and frames >= lens[b] are zero). */
 int styler_f0_norm_fwd(const float* f0, const int64_t* lens, float* out, int32_t B, int32_t T, void* stream);
 
+/* ---- A/B switches of the library (each also read once from the environment as STYLER_<NAME>): "TC_2CTA" (CTA pairs /
+ * tcgen05 cta_group::2 for the big bf16 convolutions: 0 off, 1 where it pays, 2 wherever legal), "TC_PERSIST", "CONV_WIN",
+ * "TC_BN", "TC_SMEM_KB", "PDL", "ATTN_PERSIST".  value < 0 restores the environment / built-in default.  Affects only
+ * which kernel variant runs, never the results' contract. */
+int styler_set_tuning(const char* name, int32_t value);
+
 /* ---- Debug/tuning hook: when a device buffer of capacity_ctas*8 int64 is set, every tcgen05 conv launch with at most
  * capacity_ctas CTAs writes 8 clock64() phase stamps per CTA into it (tools/phase_timing.py); NULL disables. */
 int styler_debug_set_phase_buffer(int64_t* buf, int32_t capacity_ctas);

@@ -82,6 +82,7 @@ _SIGNATURES = {
                                c_f32, c_vp, c_vp],
     "styler_f0_norm_fwd": [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp],
     "styler_debug_set_phase_buffer": [c_vp, c_i32],
+    "styler_set_tuning": [ctypes.c_char_p, c_i32],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["styler_version", "styler_last_error", "styler_launch_count"])
 
@@ -114,6 +115,11 @@ def check(rc, what=""):
     if rc != 0:
         msg = lib().styler_last_error()
         raise RuntimeError("styler_b200 %s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def set_tuning(name, value):
+    """Flip one of the library's A/B switches at run time (styler_set_tuning); value < 0 restores the default."""
+    check(lib().styler_set_tuning(name.encode(), int(value)), "set_tuning")
 
 
 def launch_count():

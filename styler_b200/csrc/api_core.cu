@@ -28,11 +28,31 @@ int num_sms() {
   return sms;
 }
 
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("STYLER_PDL"); v = (e != nullptr && atoi(e) != 0) ? 1 : 0; }   // off by default: measured 8.71 ms/step with PDL vs 8.07 without
-  return v == 1;
+namespace {
+struct TuneDef { const char* name; int dflt, lo, hi; };
+// TC_2CTA: CTA pairs for the big bf16 convs (0 off | 1 where it pays | 2 wherever legal: tests);  TC_PERSIST: persistent conv
+// form (0 | 1 two CTAs/SM | 2 also one CTA/SM);  CONV_WIN: window kernel for <= 64-channel convs;  TC_BN / TC_SMEM_KB: tile and
+// pipeline-depth overrides;  PDL: programmatic dependent launch (off: measured 8.71 ms/step with it vs 8.07 without);
+// ATTN_PERSIST: persistent attention CTAs (0 | 1)
+const TuneDef kTune[TUNE_COUNT] = {{"TC_2CTA", 1, 0, 2}, {"TC_PERSIST", 1, 0, 2}, {"CONV_WIN", 1, 0, 1}, {"TC_BN", 0, 0, 256},
+                                   {"TC_SMEM_KB", 110, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}};
+std::atomic<int> g_tune[TUNE_COUNT];          // 0 = not resolved yet, else value + 1
+}  // namespace
+
+int tuning(Tuning t) {
+  int v = g_tune[t].load(std::memory_order_relaxed);
+  if (v == 0) {
+    const std::string env = std::string("STYLER_") + kTune[t].name;
+    const char* e = getenv(env.c_str());
+    int x = e != nullptr ? atoi(e) : kTune[t].dflt;
+    if (x < kTune[t].lo || x > kTune[t].hi) x = kTune[t].dflt;
+    v = x + 1;
+    g_tune[t].store(v, std::memory_order_relaxed);
+  }
+  return v - 1;
 }
+
+bool pdl_enabled() { return tuning(TUNE_PDL) == 1; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -122,7 +142,21 @@ int make_tmap(CUtensorMap* out, const void* base, int elem, int rank, const uint
 }  // namespace sb
 
 extern "C" {
-int styler_version(void) { return 100; }
+int styler_set_tuning(const char* name, int32_t value) {
+  using namespace sb;
+  SB_REQUIRE(name != nullptr, "set_tuning: null name");
+  for (int i = 0; i < TUNE_COUNT; ++i) {
+    if (strcmp(name, kTune[i].name) == 0) {
+      if (value < 0) { g_tune[i].store(0); return 0; }          // back to the environment / default
+      SB_REQUIRE(value >= kTune[i].lo && value <= kTune[i].hi, "set_tuning: %s=%d outside [%d, %d]", name, value, kTune[i].lo, kTune[i].hi);
+      g_tune[i].store(value + 1);
+      return 0;
+    }
+  }
+  set_error("set_tuning: unknown switch %s", name);
+  return -1;
+}
+int styler_version(void) { return 200; }
 const char* styler_last_error(void) { return sb::g_err; }
 int64_t styler_launch_count(void) { return sb::g_launch_count.load(); }
 }

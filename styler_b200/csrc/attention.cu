@@ -94,7 +94,7 @@ template <typename T> struct AttnCfg {
   static constexpr int p_bytes = pv_slices * kQ * 128;
   static constexpr int kv_stages = es == 2 ? 2 : 1;
   static constexpr int umma_k = 32 / es;
-  static constexpr size_t smem = q_bytes + kv_stages * (k_bytes + v_bytes) + p_bytes + 512 + 256;  // bf16: 2 CTAs/SM
+  static constexpr size_t smem = q_bytes + kv_stages * (k_bytes + v_bytes) + p_bytes + 512 + 256;  // bf16: 2 CTAs/SM (113.25 KB each)
 };
 
 // Pipeline (per key tile j), arranged so that the tensor pipe is off the softmax critical path.  ncu on the first
@@ -102,18 +102,30 @@ template <typename T> struct AttnCfg {
 // wait for the next S tile and 36 % in the MUFU-bound exponentials, the tensor pipe 19 % busy; TMEM reads are not a
 // limit (tools/tmem_bench.cu: 885 B/clk/SM).
 //   * a softmax warp releases the S columns as soon as the scores are in its registers (s_taken); the MMA thread issues
-//     S(j+1) right then, so it runs under the exponentials of tile j;
-//   * PV(j) is issued when P(j) lands; its completion (pv_done) is only waited for by tile j+1 just before it overwrites
+//     the NEXT tile's S right then, so it runs under the exponentials of this tile;
+//   * PV(j) is issued when P(j) lands; its completion (pv_done) is only waited for by the next tile just before it overwrites
 //     sP / rescales O - after its own TMEM load, row max and all 64 exponentials;
 //   * O never leaves TMEM inside the loop.
 // With a single K/V stage (fp32/tf32 operands) K(j+1) cannot be resident before PV(j) has drained, so that
-// instantiation issues S(j+1) after PV(j) instead.  Measured (B=64, T=1024, 4 heads, bf16): 0.176 -> 0.145 ms.
+// instantiation issues the next S after PV(j) instead.  Measured (B=64, T=1024, 4 heads, bf16): 0.176 -> 0.145 ms.
+//
+// Round 2: PERSISTENT work loop.  The round-1 kernel ran one (utterance, head, query tile) per CTA: 8 key tiles of work
+// behind a cold prologue (TMEM alloc, barrier init, Q/K/V first touch ~2-5 k clk) and a drain (merge, exit barrier): the
+// source-level ncu samples put 14 % of the softmax warps' time on the FIRST s_full wait of a CTA and 8 % on the exit
+// (profiles/ncu_attn_r2.md).  Now a CTA walks work items item = blockIdx.x + i * gridDim.x with the K/V ring, the S / P /
+// PV hand-shakes and the TMEM accumulators running across item boundaries as one flat sequence of key tiles: the Q tile
+// of the next item is fetched as soon as the last S MMA of this item has been issued, and the first S of the next item
+// runs under the exponentials of this item's last tile.  (grid = number of items gives back the one-item form.)
+struct AttnItem {
+  int b, h, t0, len, nkt;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK,
                                                                       const __grid_constant__ CUtensorMap tmVT,
                                                                       const int64_t* __restrict__ lens, T* __restrict__ ctx,
                                                                       long long ctx_bs, int ctx_ld, int Tlen, int H,
-                                                                      int q_tiles, int v_mn) {
+                                                                      int q_tiles, int v_mn, int total_items) {
   using C = AttnCfg<T>;
   constexpr bool kTf32 = C::es == 4;
   extern __shared__ uint8_t smem_raw[];
@@ -125,11 +137,12 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                       // [2]
   uint64_t* kv_empty = bars + 3;                      // [2]
-  uint64_t* s_full = bars + 5;                        // MMA -> softmax: S(j) complete in TMEM
-  uint64_t* s_taken = bars + 6;                       // softmax -> MMA: S(j) is in registers, its TMEM columns may be overwritten
-  uint64_t* p_ready = bars + 7;                       // softmax -> MMA: P(j) is in smem (and O rescaled if needed)
-  uint64_t* pv_done = bars + 8;                       // MMA -> softmax: PV(j) drained: sP may be rewritten, O may be rescaled
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* s_full = bars + 5;                        // MMA -> softmax: S complete in TMEM
+  uint64_t* s_taken = bars + 6;                       // softmax -> MMA: S is in registers, its TMEM columns may be overwritten
+  uint64_t* p_ready = bars + 7;                       // softmax -> MMA: P is in smem (and O rescaled if needed)
+  uint64_t* pv_done = bars + 8;                       // MMA -> softmax: PV drained: sP may be rewritten, O may be rescaled / read
+  uint64_t* q_empty = bars + 9;                       // MMA -> producer: the last S of an item has read sQ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   if (threadIdx.x == 0 && static_cast<size_t>(reinterpret_cast<uint8_t*>(tmem_slot + 1) - smem_raw) > C::smem) {
     printf("styler_b200: attention smem carve-up overflows the allocation (base misaligned)\n");
     __trap();
@@ -139,19 +152,24 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
   auto bwait_long = [](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };   // producer / MMA threads: parked in hardware
   constexpr bool kEarlyS = C::kv_stages >= 2;         // K(j+1) can be resident while V(j) is still needed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % q_tiles;
-  const int h = (blockIdx.x / q_tiles) % H;
-  const int b = blockIdx.x / (q_tiles * H);
-  const int t0 = qt * kQ;
-  int len = lens != nullptr ? static_cast<int>(lens[b]) : Tlen;
-  len = len < Tlen ? len : Tlen;
-  const int nkt = (len + kKV - 1) / kKV;
   const int D = H * 64;
+  auto item_at = [&](int item) {                      // every role decodes the same item sequence
+    AttnItem it;
+    const int qt = item % q_tiles;
+    it.h = (item / q_tiles) % H;
+    it.b = item / (q_tiles * H);
+    it.t0 = qt * kQ;
+    int len = lens != nullptr ? static_cast<int>(lens[it.b]) : Tlen;
+    it.len = len < Tlen ? len : Tlen;
+    it.nkt = (it.len + kKV - 1) / kKV;
+    return it;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmVT);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
     mbar_init(s_taken, 8);                            // one elected arrival per softmax warp
@@ -169,39 +187,61 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
   pdl_grid_dependency_wait();     // the QKV projection (previous kernel) is complete and visible from here on
 
   if (warp == 0) {
-    if (lane == 0 && nkt > 0) {
-      mbar_arrive_expect_tx(q_full, C::q_bytes);
-      for (int sl = 0; sl < C::qk_slices; ++sl)
-        tma_load_3d(sQ + sl * kQ * 128, &tmQK, q_full, h * 64 + sl * C::bke, t0, b);
-      for (int j = 0; j < nkt; ++j) {
-        const int s = j % C::kv_stages;
-        const uint32_t ph = (j / C::kv_stages) & 1;
-        bwait_long(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], C::k_bytes + C::v_bytes);
-        uint8_t* sK = sKV + s * (C::k_bytes + C::v_bytes);
-        uint8_t* sV = sK + C::k_bytes;
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int qi = 0, g = 0;                               // items with key tiles seen so far; key tiles loaded so far (ring position)
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const AttnItem it = item_at(item);
+        if (it.nkt == 0) continue;
+        if (qi > 0) bwait_long(q_empty, (qi - 1) & 1);  // the previous item's last S MMA has consumed sQ
+        mbar_arrive_expect_tx(q_full, C::q_bytes);
         for (int sl = 0; sl < C::qk_slices; ++sl)
-          tma_load_3d(sK + sl * kKV * 128, &tmQK, &kv_full[s], D + h * 64 + sl * C::bke, j * kKV, b);
-        if (v_mn) {   // V row-major in the qkv tensor: [128 keys x 128-byte span of d] boxes, consumed as an MN-major B operand
+          tma_load_3d(sQ + sl * kQ * 128, &tmQK, q_full, it.h * 64 + sl * C::bke, it.t0, it.b);
+        ++qi;
+        for (int j = 0; j < it.nkt; ++j, ++g) {
+          const int s = g % C::kv_stages;
+          const uint32_t ph = (g / C::kv_stages) & 1;
+          bwait_long(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], C::k_bytes + C::v_bytes);
+          uint8_t* sK = sKV + s * (C::k_bytes + C::v_bytes);
+          uint8_t* sV = sK + C::k_bytes;
           for (int sl = 0; sl < C::qk_slices; ++sl)
-            tma_load_3d(sV + sl * kKV * 128, &tmQK, &kv_full[s], 2 * D + h * 64 + sl * C::bke, j * kKV, b);
-        } else {
-          for (int sl = 0; sl < C::pv_slices; ++sl)
-            tma_load_3d(sV + sl * 64 * 128, &tmVT, &kv_full[s], j * kKV + sl * C::bke, h * 64, b);
+            tma_load_3d(sK + sl * kKV * 128, &tmQK, &kv_full[s], D + it.h * 64 + sl * C::bke, j * kKV, it.b);
+          if (v_mn) {   // V row-major in the qkv tensor: [128 keys x 128-byte span of d] boxes, consumed as an MN-major B operand
+            for (int sl = 0; sl < C::qk_slices; ++sl)
+              tma_load_3d(sV + sl * kKV * 128, &tmQK, &kv_full[s], 2 * D + it.h * 64 + sl * C::bke, j * kKV, it.b);
+          } else {
+            for (int sl = 0; sl < C::pv_slices; ++sl)
+              tma_load_3d(sV + sl * 64 * 128, &tmVT, &kv_full[s], j * kKV + sl * C::bke, it.h * 64, it.b);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nkt > 0) {
+    // ------------------------------------------------------------------ MMA issuer: one flat sequence of key tiles
+    if (lane == 0) {
       const uint32_t fmt = kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16;
       const uint32_t idesc_s = umma_idesc(fmt, kQ, kKV);
       const uint32_t idesc_o = umma_idesc(fmt, kQ, 64, v_mn ? 1u : 0u);
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
       constexpr int kPvSteps = kKV / C::umma_k;          // K steps of the PV product (bf16 8, tf32 16)
-      auto issue_s = [&](int j) {
-        const int s = j % C::kv_stages;
-        bwait_long(&kv_full[s], (j / C::kv_stages) & 1);
+      // cursor over (item, key tile); `g` = key tiles issued so far (ring position), `qi` = items started
+      int item_c = blockIdx.x, nkt_c = 0, j_c = 0;       // current tile (whose PV is next)
+      auto next_item_with_tiles = [&](int item, int& nkt) {
+        for (; item < total_items; item += gridDim.x) {
+          nkt = item_at(item).nkt;
+          if (nkt > 0) return item;
+        }
+        nkt = 0;
+        return total_items;
+      };
+      item_c = next_item_with_tiles(item_c, nkt_c);
+      int gs = 0, qi = 0;                                // S tiles issued, items whose Q has been waited for
+      auto issue_s = [&](bool first_of_item, bool last_of_item) {
+        if (first_of_item) { bwait_long(q_full, qi & 1); ++qi; }
+        const int s = gs % C::kv_stages;
+        bwait_long(&kv_full[s], (gs / C::kv_stages) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sKV + s * (C::k_bytes + C::v_bytes));
 #pragma unroll
@@ -211,18 +251,24 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
                          umma_desc_k_sw128(k_addr + sl * kKV * 128 + off), idesc_s, kk != 0 ? 1u : 0u);
         }
         umma_commit(s_full);
+        if (last_of_item) umma_commit(q_empty);          // sQ may be refilled once this MMA has completed
+        ++gs;
       };
-      bwait_long(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nkt; ++j) {
-        const int s = j % C::kv_stages;
+      if (item_c < total_items) issue_s(true, nkt_c == 1);
+      int g = 0;                                         // PV tiles issued
+      while (item_c < total_items) {
+        // the tile after (item_c, j_c) in the flat sequence
+        int item_n = item_c, nkt_n = nkt_c, j_n = j_c + 1;
+        if (j_n == nkt_c) { j_n = 0; item_n = next_item_with_tiles(item_c + static_cast<int>(gridDim.x), nkt_n); }
+        const bool has_next = item_n < total_items;
+        const int s = g % C::kv_stages;
         const uint32_t v_addr = smem_u32(sKV + s * (C::k_bytes + C::v_bytes)) + C::k_bytes;
-        if (kEarlyS && j + 1 < nkt) {                    // S(j+1) runs under the exponentials of tile j
-          bwait_long(s_taken, j & 1);
+        if (kEarlyS && has_next) {                       // the next S runs under the exponentials of this tile
+          bwait_long(s_taken, g & 1);
           tc_fence_after();
-          issue_s(j + 1);
+          issue_s(j_n == 0, j_n == nkt_n - 1);
         }
-        bwait_long(p_ready, j & 1);
+        bwait_long(p_ready, g & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kPvSteps; ++kk) {
@@ -231,30 +277,38 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
           const uint64_t bdesc = v_mn ? umma_desc_mn_sw128(v_addr + kk * C::umma_k * 128, kKV * 128, 1024)
                                       : umma_desc_k_sw128(v_addr + sl * 64 * 128 + off);
           umma_ss<kTf32>(tmem_O + half * 64, umma_desc_k_sw128(p_addr + sl * kQ * 128 + off), bdesc, idesc_o,
-                         (j != 0 || (kk % (kPvSteps / 2)) != 0) ? 1u : 0u);
+                         (j_c != 0 || (kk % (kPvSteps / 2)) != 0) ? 1u : 0u);
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[s]);
-        if (!kEarlyS && j + 1 < nkt) issue_s(j + 1);     // single K/V stage: K(j+1) can only land after PV(j)
+        ++g;
+        if (!kEarlyS && has_next) issue_s(j_n == 0, j_n == nkt_n - 1);   // single K/V stage: K(next) can only land after PV
+        item_c = item_n; nkt_c = nkt_n; j_c = j_n;
       }
     }
     __syncwarp();
   } else {
+    // ------------------------------------------------------------------ softmax warps
     const int q = warp & 3;                            // TMEM lane quarter this warp may touch
     const int hf = (warp - 2) >> 2;                    // key half (64 of the tile's 128 score columns) owned by this thread
     const int r = q * 32 + lane;
-    const int t = t0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tS = tmem_S + lane_off + hf * 64;
     const uint32_t tO = tmem_O + lane_off + hf * 64;
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kRescale = 8.0f;                   // raise the running max only when it is stale by > 2^8
-    float m_l = -INFINITY;                             // running (stale) max, log2 domain
-    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;      // row sum of this key half (4 chains)
     uint8_t* p_row = sP + r * 128;
     const int sw = r & 7;
-    for (int j = 0; j < nkt; ++j) {
-      bwait(s_full, j & 1);
+    float2* s_ml = reinterpret_cast<float2*>(sP);      // half-merge exchange; sP is dead between an item's last PV and the next P
+    int g = 0;                                         // key tiles processed so far (barrier phases run across items)
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const AttnItem it = item_at(item);
+    const int nkt = it.nkt, len = it.len;
+    const int t = it.t0 + r;
+    float m_l = -INFINITY;                             // running (stale) max, log2 domain
+    float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);   // row sum of this key half (two packed chains)
+    for (int j = 0; j < nkt; ++j, ++g) {
+      bwait(s_full, g & 1);
       tc_fence_after();
       const int kbase = j * kKV + hf * 64;
       const bool full_tile = kbase + 64 <= len;        // only the last key tile needs the padding mask
@@ -269,7 +323,7 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_taken);               // S(j) is in registers: the MMA thread may start S(j+1)
+      if (lane == 0) mbar_arrive(s_taken);               // S is in registers: the MMA thread may start the next S
       float mx0 = -INFINITY, mx1 = -INFINITY;
       if (full_tile) {
 #pragma unroll
@@ -289,28 +343,37 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
       if (any_raise) {
         const float m_new = raise ? mx_l : m_l;
         alpha = m_l == -INFINITY ? 0.f : fast_exp2(m_l - m_new);   // 1 for the lanes that keep their max
-        l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+        const float2 a2 = make_float2(alpha, alpha);
+        l01 = __fmul2_rn(l01, a2); l23 = __fmul2_rn(l23, a2);
         m_l = m_new;
       }
-      // exponentials in place (sv[i] <- bits of p_i): everything up to here overlaps PV(j-1) and S(j+1) on the tensor pipe
-      if (full_tile) {
+      // exponentials in place (sv[i] <- bits of p_i): everything up to here overlaps the previous PV and the next S on the
+      // tensor pipe.  x = s * log2(e) - m on packed FFMA2 (two scores per issue slot), then MUFU.EX2.
+      {
+        const float2 k2 = make_float2(kLog2e, kLog2e), nm2 = make_float2(-m_l, -m_l);
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const float x = fmaf(__uint_as_float(sv[i]), kLog2e, -m_l);
-          sv[i] = __float_as_uint(fast_exp2(x));
+          for (int i = 0; i < 64; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), k2, nm2);
+            sv[i] = __float_as_uint(fast_exp2(x.x));
+            sv[i + 1] = __float_as_uint(fast_exp2(x.y));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), k2, nm2);
+            sv[i] = __float_as_uint(kbase + i < len ? fast_exp2(x.x) : 0.f);
+            sv[i + 1] = __float_as_uint(kbase + i + 1 < len ? fast_exp2(x.y) : 0.f);
+          }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          sv[i] = __float_as_uint(kbase + i < len ? fast_exp2(fmaf(__uint_as_float(sv[i]), kLog2e, -m_l)) : 0.f);
       }
 #pragma unroll
       for (int i = 0; i < 64; i += 4) {
-        l0 += __uint_as_float(sv[i]); l1 += __uint_as_float(sv[i + 1]);
-        l2 += __uint_as_float(sv[i + 2]); l3 += __uint_as_float(sv[i + 3]);
+        l01 = __fadd2_rn(l01, make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+        l23 = __fadd2_rn(l23, make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
       }
       if (j > 0) {                                     // PV(j-1) must have drained before sP is rewritten / O rescaled
-        bwait(pv_done, (j - 1) & 1);
+        bwait(pv_done, (g - 1) & 1);                   // (j == 0: the previous item's last PV was waited for by its merge)
         tc_fence_after();
         if (any_raise) {
 #pragma unroll 1
@@ -339,9 +402,9 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
           store8(reinterpret_cast<__nv_bfloat16*>(slice + (((ch0 + 1) ^ sw) * 16)), a1);
         } else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(slice + (((ch0 + g) ^ sw) * 16)) =
-                make_uint4(sv[cc + 4 * g], sv[cc + 4 * g + 1], sv[cc + 4 * g + 2], sv[cc + 4 * g + 3]);
+          for (int gq = 0; gq < 4; ++gq)
+            *reinterpret_cast<uint4*>(slice + (((ch0 + gq) ^ sw) * 16)) =
+                make_uint4(sv[cc + 4 * gq], sv[cc + 4 * gq + 1], sv[cc + 4 * gq + 2], sv[cc + 4 * gq + 3]);
         }
       }
       fence_proxy_async_smem();
@@ -350,22 +413,23 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
       if (lane == 0) mbar_arrive(p_ready);
     }
     // merge the two key halves: out = (O_a w_a + O_b w_b) / (l_a w_a + l_b w_b), w_x = 2^(m_x - max(m_a, m_b)).
-    // The exchange goes through smem (the Q tile is dead once the last S MMA has completed).
-    float2* s_ml = reinterpret_cast<float2*>(sQ);
+    // The exchange goes through sP (dead once the item's last PV has completed; the next item's first P is only written
+    // after the second barrier below).
     if (nkt > 0) {
-      bwait(pv_done, (nkt - 1) & 1);
+      bwait(pv_done, (g - 1) & 1);
       tc_fence_after();
     }
-    s_ml[hf * kQ + r] = make_float2(m_l, (l0 + l1) + (l2 + l3));
+    s_ml[hf * kQ + r] = make_float2(m_l, (l01.x + l01.y) + (l23.x + l23.y));
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float2 ma = s_ml[r], mb = s_ml[kQ + r];
+    asm volatile("bar.sync 1, 256;" ::: "memory");    // both halves have read the exchange: sP may take the next item's P
     const float m_tot = fmaxf(ma.x, mb.x);
     const float wa = ma.x == -INFINITY ? 0.f : fast_exp2(ma.x - m_tot);
     const float wb = mb.x == -INFINITY ? 0.f : fast_exp2(mb.x - m_tot);
     const float l_tot = ma.y * wa + mb.y * wb;
     const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
     const float fa = wa * inv, fb = wb * inv;
-    T* orow = ctx + b * ctx_bs + static_cast<long long>(t) * ctx_ld + h * 64 + hf * 32;
+    T* orow = ctx + it.b * ctx_bs + static_cast<long long>(t) * ctx_ld + it.h * 64 + hf * 32;
 #pragma unroll
     for (int c = 0; c < 32; c += 16) {
       float o[16];
@@ -390,6 +454,8 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
         store8(orow + c + 8, v1);
       }
     }
+    tc_fence_before();                                 // this item's O reads are ordered before the p_ready arrive that lets the
+    }   // item loop                                   // next item's first PV overwrite the accumulators
   }
   tc_fence_before();
   __syncthreads();
@@ -423,8 +489,13 @@ int launch_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t 
   static DeviceFlags attr_set;
   SB_OPT_IN_SMEM(attr_set, kern, C::smem);
   const int q_tiles = ceil_div(Tlen, kQ);
-  SB_CUDA_OK(launch_pdl(kern, dim3(B * H * q_tiles), dim3(kThreadsTc), C::smem, s, tmQK, tmVT, lens, static_cast<T*>(ctx),
-                        static_cast<long long>(ctx_bs), ctx_ld, Tlen, H, q_tiles, v_mn));
+  const long long total = static_cast<long long>(B) * H * q_tiles;
+  SB_REQUIRE(total < (1LL << 30), "attention_tc: too many work items");
+  // persistent: one resident CTA per slot (two per SM for bf16 operands, one for fp32) walks the items; ATTN_PERSIST=0 -> one item per CTA
+  const int slots = (C::es == 2 ? 2 : 1) * num_sms();
+  const int grid = (tuning(TUNE_ATTN_PERSIST) != 0 && total > slots) ? slots : static_cast<int>(total);
+  SB_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kThreadsTc), C::smem, s, tmQK, tmVT, lens, static_cast<T*>(ctx),
+                        static_cast<long long>(ctx_bs), ctx_ld, Tlen, H, q_tiles, v_mn, static_cast<int>(total)));
   SB_LAUNCH_OK();
   return 0;
 }

@@ -30,6 +30,11 @@ struct DeviceFlags {
 };
 int num_sms();   // SM count of the current device (cached per device)
 
+// A/B switches: read once from the environment (STYLER_<NAME>), overridable at run time through styler_set_tuning()
+// (tests and tools/prof_kernels.py flip them inside one process).
+enum Tuning { TUNE_TC_2CTA = 0, TUNE_TC_PERSIST, TUNE_CONV_WIN, TUNE_TC_BN, TUNE_TC_SMEM_KB, TUNE_PDL, TUNE_ATTN_PERSIST, TUNE_COUNT };
+int tuning(Tuning t);
+
 #define SB_OPT_IN_SMEM(flags, kern, bytes)                                                                     \
   do {                                                                                                         \
     const int dev__ = ::sb::current_device();                                                                  \
@@ -139,6 +144,23 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// Launch as thread-block clusters of two consecutive CTAs along x (CTA pairs for tcgen05 cta_group::2).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster2(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);

@@ -71,6 +71,44 @@ __device__ __forceinline__ void store16(T* p, const float (&v)[16]) {
   store8(p + 8, b);
 }
 
+// Packed fp32 arithmetic (FADD2 / FFMA2, sm_100: two lanes of work per issue slot; the FMA pipe accepts one warp instruction
+// every 2 clk, and these epilogues are bound by instruction issue, not by memory -- profiles/prof_kernels_r1e.txt).
+__device__ __forceinline__ void add16(float (&v)[16], const float (&b)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float2 r = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b[i], b[i + 1]));
+    v[i] = r.x; v[i + 1] = r.y;
+  }
+}
+__device__ __forceinline__ void add16_bits(float (&v)[16], const uint32_t (&a)[16], const float (&b)[16]) {   // v = a + b
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float2 r = __fadd2_rn(make_float2(__uint_as_float(a[i]), __uint_as_float(a[i + 1])), make_float2(b[i], b[i + 1]));
+    v[i] = r.x; v[i + 1] = r.y;
+  }
+}
+// shifted sums for LayerNorm: s1 += (v - shift), s2 += (v - shift)^2, two packed chains
+__device__ __forceinline__ void stats16(const float (&v)[16], float shift, float2 (&s1)[2], float2 (&s2)[2]) {
+  const float2 ns = make_float2(-shift, -shift);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float2 d = __fadd2_rn(make_float2(v[i], v[i + 1]), ns);
+    s1[(i >> 1) & 1] = __fadd2_rn(s1[(i >> 1) & 1], d);
+    s2[(i >> 1) & 1] = __ffma2_rn(d, d, s2[(i >> 1) & 1]);
+  }
+}
+// v = ((x * rstd + nmr) * gamma + beta)
+__device__ __forceinline__ void norm16(float (&v)[16], const uint32_t (&x)[16], float rstd, float nmr, const float (&g)[16],
+                                       const float (&b)[16]) {
+  const float2 r2 = make_float2(rstd, rstd), n2 = make_float2(nmr, nmr);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float2 t = __ffma2_rn(make_float2(__uint_as_float(x[i]), __uint_as_float(x[i + 1])), r2, n2);
+    const float2 r = __ffma2_rn(t, make_float2(g[i], g[i + 1]), make_float2(b[i], b[i + 1]));
+    v[i] = r.x; v[i + 1] = r.y;
+  }
+}
+
 // ACT (activation before residual/LN) and LN are compile-time so each instance carries one tight epilogue loop: the
 // generic runtime-switched body was ~1850 SASS instructions per 32 columns (tanhf inlined 64x) and ran at ~7 clk/instr.
 // FAST: output staged through smem + TMA store, residual (if any) staged through smem, no V^T / fp32 copy / row dot:
@@ -80,7 +118,12 @@ __device__ __forceinline__ void store16(T* p, const float (&v)[16]) {
 // running on across tile boundaries.  The loads and MMAs of tile i+1 then overlap the epilogue and the TMA store of tile
 // i inside one CTA: with K <= 1024 a tile's mainloop (2-8 k cycles of MMA) is shorter than its TMA round trip plus its
 // epilogue (~6 k cycles), which the one-tile-per-CTA form pays serially (phase stamps: profiles/phase_timing_r1c.txt).
-template <typename T, int ACT, bool LN, bool FAST, bool PERSIST>
+// CG2 (bf16, FAST, non-persistent, BN = 256): CTA pairs.  A cluster of two CTAs owns two vertically adjacent
+// 128-row tiles of the same N tile; each CTA stages its own A rows and 128 of the 256 weight rows, the leader issues
+// tcgen05.mma.cta_group::2 (M = 256) and every CTA runs the epilogue of its own 128 accumulator rows (ptx.cuh).  The big
+// convolutions are bound by the operand bytes each SM has to pull from L2 (FFN k9: 48 KB per 128x256x64 k-block,
+// 15.5 TB/s chip-wide at 0.455 ms); the pair needs 32 KB per SM for the same MMA work.
+template <typename T, int ACT, bool LN, bool FAST, bool PERSIST, bool CG2 = false>
 __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmOut,
@@ -89,13 +132,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
                                                              int tiles_per_utt, int KS, int pad, int kb_per_tap,
                                                              int BN, int stages, int total_tiles, int dil) {
   static_assert(!PERSIST || FAST, "the persistent tile loop only exists for the staged (FAST) epilogue");
+  static_assert(!CG2 || (FAST && !PERSIST && sizeof(T) == 2), "CTA pairs: bf16, staged epilogue, one tile per CTA");
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int kBKE = 128 / sizeof(T);  // elements per 128-byte k-slice
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int b_stage_bytes = BN * 128;
+  const int b_stage_bytes = (CG2 ? BN / 2 : BN) * 128;           // CTA pair: this CTA holds half of the weight rows
   const int stage_bytes = kAStageBytes + b_stage_bytes;
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;        // 0 = leader (issues the MMAs of the pair)
   const int n_box = (BN * static_cast<int>(sizeof(T))) / 128;     // 16 KB [128 rows x 128 B] boxes per output tile
   // epilogue staging (output rows / residual rows): its own region when persistent, the idle operand ring otherwise
   uint8_t* stg = PERSIST ? smem + stages * stage_bytes : smem;
@@ -116,6 +161,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
   const uint32_t acc_cols = tmem_cols_pow2(BN);                      // columns of one accumulator
   const uint32_t tmem_cols = PERSIST ? 2 * acc_cols : acc_cols;
   const int tile_step = PERSIST ? static_cast<int>(gridDim.x) : total_tiles;   // non-persistent: exactly one tile per CTA
+  const int tile_first = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // CG2: total_tiles counts PAIRS
+  auto m_tile_of = [&](int tile) { return CG2 ? 2 * (tile / n_tiles) + static_cast<int>(cta_rank) : tile / n_tiles; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -125,9 +172,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     mbar_init(res_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 1) { if (CG2) tmem_alloc_2cta(tmem_slot, tmem_cols); else tmem_alloc(tmem_slot, tmem_cols); }
   tc_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync_all();     // the peer's barriers are initialised before any remote arrive / complete_tx can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();        // the next kernel may start its prologue in SM slots this grid no longer needs
@@ -138,18 +186,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int g = 0;                                   // k-block counter over all tiles of this CTA: the ring never drains
-      for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step) {
-        const int nt = tile % n_tiles, mt = tile / n_tiles;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const int nt = tile % n_tiles, mt = m_tile_of(tile);
         const int b = mt / tiles_per_utt, t0 = (mt % tiles_per_utt) * kBM, n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           const int s = g % stages;
           const uint32_t ph = (g / stages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], stage_bytes);
           const int tap = kb / kb_per_tap, kc = (kb % kb_per_tap) * kBKE;
           uint8_t* sa = smem + s * stage_bytes;
-          tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap * dil - pad, b);
-          tma_load_3d(sa + kAStageBytes, &tmB, &full[s], kc, n0, tap);
+          if constexpr (CG2) {
+            // both CTAs of the pair credit the LEADER's full barrier; only the leader arms it (with the bytes of both)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * stage_bytes);
+            const uint32_t bar = leader_cta_addr(smem_u32(&full[s]));
+            tma_load_3d_2cta(sa, &tmA, bar, kc, t0 + tap * dil - pad, b);
+            tma_load_3d_2cta(sa + kAStageBytes, &tmB, bar, kc, n0 + static_cast<int>(cta_rank) * (BN / 2), tap);
+          } else {
+            mbar_arrive_expect_tx(&full[s], stage_bytes);
+            tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap * dil - pad, b);
+            tma_load_3d(sa + kAStageBytes, &tmB, &full[s], kc, n0, tap);
+          }
         }
         if (!PERSIST && (FAST ? ep.residual != nullptr : ep.stage_res != 0)) {
           // all MMAs done -> the pipeline stages are free: stage the residual tile there
@@ -162,10 +218,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, kBM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, CG2 ? 2 * kBM : kBM, BN);
       int g = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step, ++it) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
         const int ab = PERSIST ? (it & 1) : 0;
         const uint32_t acc = tmem_base + ab * acc_cols;
         if (PERSIST) {                             // the epilogue has drained this accumulator (tile it-2)
@@ -182,12 +238,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
           const uint32_t b_addr = a_addr + kAStageBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte slice
-            umma_ss<kTf32>(acc, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG2)
+              umma_ss_2cta_f16(acc, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_ss<kTf32>(acc, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          if constexpr (CG2) umma_commit_2cta(&empty[s], 3); else umma_commit(&empty[s]);   // pair: frees the stage in BOTH CTAs
         }
-        umma_commit(&tmem_full[ab]);
+        if constexpr (CG2) umma_commit_2cta(&tmem_full[ab], 3); else umma_commit(&tmem_full[ab]);
         if (dbg != nullptr) dbg[3] = clock64();
       }
     }
@@ -203,15 +263,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     const int c_begin = split ? hf * (BN / 2) : (hf == 0 ? 0 : BN);
     const int c_end = split ? c_begin + BN / 2 : BN;
     int it = 0;
-    if (PERSIST && ep.residual != nullptr && threadIdx.x == 64 && static_cast<int>(blockIdx.x) < total_tiles) {
+    if (PERSIST && ep.residual != nullptr && threadIdx.x == 64 && static_cast<int>(blockIdx.x) < total_tiles) {   // (never CG2)
       // residual rows of this CTA's first tile -> staging buffer (later tiles: issued when the previous store has drained)
       const int nt = blockIdx.x % n_tiles, mt = blockIdx.x / n_tiles;
       mbar_arrive_expect_tx(res_full, n_box * kAStageBytes);
       for (int bx = 0; bx < n_box; ++bx)
         tma_load_3d(stg + bx * kAStageBytes, &tmRes, res_full, nt * BN + bx * kBKE, (mt % tiles_per_utt) * kBM, mt / tiles_per_utt);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step, ++it) {
-    const int nt = tile % n_tiles, mt = tile / n_tiles;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
+    const int nt = tile % n_tiles, mt = m_tile_of(tile);
     const int b = mt / tiles_per_utt, t0 = (mt % tiles_per_utt) * kBM;
     const int n0 = nt * BN;
     const int ab = PERSIST ? (it & 1) : 0;
@@ -355,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       // pass 1: v = act(acc + bias) + residual, parked back in TMEM; shifted sums for mean/variance.
       // Two 16-column chunks per iteration so TMEM and residual loads of both are in flight together.
       float shift = 0.f;
-      float s1p[4] = {0.f, 0.f, 0.f, 0.f}, s2p[4] = {0.f, 0.f, 0.f, 0.f};   // 4 chains each: 16 dependent FADD/FFMA per chunk otherwise
+      float2 s1p[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, s2p[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       for (int c = c_begin; c < c_end; c += 32) {
         const bool two = c + 16 < c_end;
         uint32_t ra[16], rb[16];
@@ -368,37 +428,31 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
         {
           float v[16], pb[16];
           ld16s(s_bias + c, pb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + pb[i];
+          add16_bits(v, ra, pb);
           act1(v);
-          if (do_res) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += xa[i];
-          }
+          if (do_res) add16(v, xa);
           if (c == c_begin) shift = v[0];
+          stats16(v, shift, s1p, s2p);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1p[i & 3] += d; s2p[i & 3] = fmaf(d, d, s2p[i & 3]); ra[i] = __float_as_uint(v[i]); }
+          for (int i = 0; i < 16; ++i) ra[i] = __float_as_uint(v[i]);
           tmem_st16(taddr + c, ra);
         }
         if (two) {
           float v[16], pb[16];
           ld16s(s_bias + c + 16, pb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + pb[i];
+          add16_bits(v, rb, pb);
           act1(v);
-          if (do_res) {
+          if (do_res) add16(v, xb);
+          stats16(v, shift, s1p, s2p);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += xb[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { const float d = v[i] - shift; s1p[i & 3] += d; s2p[i & 3] = fmaf(d, d, s2p[i & 3]); rb[i] = __float_as_uint(v[i]); }
+          for (int i = 0; i < 16; ++i) rb[i] = __float_as_uint(v[i]);
           tmem_st16(taddr + c + 16, rb);
         }
       }
       tmem_st_wait();
       // combine the two half-row statistics (shifted sums are merged exactly; n_h = columns owned by half h)
       float* mine = s_x + (hf * 128 + r) * 4;
-      mine[0] = shift; mine[1] = (s1p[0] + s1p[1]) + (s1p[2] + s1p[3]); mine[2] = (s2p[0] + s2p[1]) + (s2p[2] + s2p[3]);
+      mine[0] = shift; mine[1] = (s1p[0].x + s1p[0].y) + (s1p[1].x + s1p[1].y); mine[2] = (s2p[0].x + s2p[0].y) + (s2p[1].x + s2p[1].y);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* h0 = s_x + r * 4;
       const float* h1 = s_x + (128 + r) * 4;
@@ -458,17 +512,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       if (has_ln) {
         ld16s(s_gamma + c, pa);
         ld16s(s_beta + c, pb);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(fmaf(__uint_as_float(ra[i]), rstd, nmr), pa[i], pb[i]);
+        norm16(v, ra, rstd, nmr, pa, pb);
       } else {
         ld16s(s_bias + c, pb);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + pb[i];
+        add16_bits(v, ra, pb);
         act1(v);
-        if (need_res) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += xa[i];
-        }
+        if (need_res) add16(v, xa);
       }
       act2f(v);
       finish_chunk(c, v);
@@ -476,17 +525,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
         if (has_ln) {
           ld16s(s_gamma + c + 16, pa);
           ld16s(s_beta + c + 16, pb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaf(fmaf(__uint_as_float(rb[i]), rstd, nmr), pa[i], pb[i]);
+          norm16(v, rb, rstd, nmr, pa, pb);
         } else {
           ld16s(s_bias + c + 16, pb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]) + pb[i];
+          add16_bits(v, rb, pb);
           act1(v);
-          if (need_res) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += xb[i];
-          }
+          if (need_res) add16(v, xb);
         }
         act2f(v);
         finish_chunk(c + 16, v);
@@ -527,34 +571,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (CG2) cluster_sync_all();     // neither CTA may exit (or free TMEM) while the pair's MMAs / multicast arrivals can still touch it
+  if (warp == 1) { if (CG2) tmem_dealloc_2cta(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols); }
   if (dbg != nullptr && threadIdx.x == 0) dbg[7] = clock64();
 }
 
-int smem_budget_bytes() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("STYLER_TC_SMEM_KB");
-    v = (e != nullptr ? atoi(e) : 110) * 1024;
-    if (v < 64 * 1024) v = 64 * 1024;
-    if (v > 220 * 1024) v = 220 * 1024;
-  }
-  return v;
-}
-
-// STYLER_TC_PERSIST: 0 = one tile per CTA everywhere, 1 (default) = persistent form where two CTAs per SM still fit
-// (two accumulators of <= 128 TMEM columns), 2 = also the one-CTA-per-SM form (N = 256 LayerNorm rows; measured slower:
-// out-proj 0.037 -> 0.045 ms, its epilogue is issue-bound and loses the second CTA's warps).
-int persist_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("STYLER_TC_PERSIST"); v = e != nullptr ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
-  return v;
-}
+int smem_budget_bytes() { return tuning(TUNE_TC_SMEM_KB) * 1024; }
+// persistent form: 0 = one tile per CTA everywhere, 1 (default) = where two CTAs per SM still fit (two accumulators of <= 128
+// TMEM columns), 2 = also the one-CTA-per-SM form (N = 256 LayerNorm rows; measured slower: out-proj 0.037 -> 0.045 ms, its
+// epilogue is issue-bound and loses the second CTA's warps)
+int persist_mode() { return tuning(TUNE_TC_PERSIST); }
+// CTA pairs (cta_group::2, M = 256) for the big bf16 convolutions: 0 = never, 1 (default) = where it pays, 2 = wherever legal
+int cg2_mode() { return tuning(TUNE_TC_2CTA); }
 
 int pick_bn(const styler_conv1d_args& a, int m_tiles) {
   if (a.ln_gamma != nullptr || a.dot_w != nullptr) return (a.N <= 256 && a.N % 16 == 0) ? a.N : 0;
-  static int forced = -1;   // tuning override: STYLER_TC_BN
-  if (forced < 0) { const char* e = getenv("STYLER_TC_BN"); forced = e != nullptr ? atoi(e) : 0; }
+  const int forced = tuning(TUNE_TC_BN);   // tuning override: STYLER_TC_BN
   if (forced > 0 && forced % 16 == 0 && forced <= 256 && a.N % forced == 0 && (a.vt == nullptr || a.vt_col0 % forced == 0))
     return forced;
   // Prefer tiles whose rows are whole 128-byte boxes (coalesced TMA epilogue); among those the largest tile that still
@@ -607,7 +639,12 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   SB_REQUIRE(BN > 0, "conv1d_tc: no valid N tile for N=%d", a.N);
   const int n_tiles = a.N / BN;
   const int total_tiles = m_tiles * n_tiles;
-  const int stage_bytes = kAStageBytes + BN * 128;
+  // CTA pairs (see the kernel comment): long mainloops on a 256-wide N tile, staged epilogue without residual, an even number
+  // of M tiles, and enough tiles that pairing costs no occupancy
+  // (LayerNorm rows, N = 256, included: their B tile is 2/3 of the operand bytes and their 48 KB stages only fit twice)
+  const bool cg2 = cg2_mode() != 0 && es == 2 && !persist && fast_like && BN == 256 && (m_tiles % 2) == 0 &&
+                   (cg2_mode() == 2 || (num_kb >= 4 && total_tiles >= 2 * num_sms()));
+  const int stage_bytes = kAStageBytes + (cg2 ? BN / 2 : BN) * 128;
   const int staging_bytes = persist ? BN * es * kBM : 0;
   const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/ + 4096 /*exchange*/;
   int stages = ((persist ? (ctas_per_sm == 2 ? 113 : 226) * 1024 - staging_bytes - fixed_bytes : smem_budget_bytes())) / stage_bytes;
@@ -629,7 +666,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(a.Cin), static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.KS)};
     const uint64_t strides[2] = {static_cast<uint64_t>(a.Cin) * es, static_cast<uint64_t>(a.Cin) * a.N * es};
-    const uint32_t box[3] = {static_cast<uint32_t>(bke), static_cast<uint32_t>(BN), 1};
+    const uint32_t box[3] = {static_cast<uint32_t>(bke), static_cast<uint32_t>(cg2 ? BN / 2 : BN), 1};
     int rc = make_tmap(&tmB, a.w, es == 2 ? 1 : 0, 3, dims, strides, box);
     if (rc != 0) return rc;
   }
@@ -684,6 +721,24 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
                      (a.residual == nullptr || stage_res)) ? 1 : 0;
   const int ip = persist ? 1 : 0;
   SB_REQUIRE(!persist || ifast == 1, "conv1d_tc: internal: persistent form chosen for a non-staged epilogue");
+  if constexpr (es == 2) {
+    if (cg2) {
+      SB_REQUIRE(ifast == 1, "conv1d_tc: internal: CTA-pair form chosen for a non-staged epilogue");
+      static const KernFn table2[4][2] = {
+          {conv1d_tc_kernel<T, STYLER_ACT_NONE, false, true, false, true>, conv1d_tc_kernel<T, STYLER_ACT_NONE, true, true, false, true>},
+          {conv1d_tc_kernel<T, STYLER_ACT_RELU, false, true, false, true>, conv1d_tc_kernel<T, STYLER_ACT_RELU, true, true, false, true>},
+          {conv1d_tc_kernel<T, STYLER_ACT_TANH, false, true, false, true>, conv1d_tc_kernel<T, STYLER_ACT_TANH, true, true, false, true>},
+          {conv1d_tc_kernel<T, STYLER_ACT_LRELU, false, true, false, true>, conv1d_tc_kernel<T, STYLER_ACT_LRELU, true, true, false, true>}};
+      static DeviceFlags attr_set2[4][2];
+      KernFn kern2 = table2[ia][il];
+      SB_OPT_IN_SMEM(attr_set2[ia][il], kern2, 227 * 1024);
+      // grid = one CTA per 128-row tile as before, launched as clusters of two; the kernel counts tiles in PAIRS
+      SB_CUDA_OK(launch_cluster2(kern2, dim3(total_tiles), dim3(kThreads), smem, stream, tmA, tmB, tmOut, tmRes, ep, a.T, n_tiles,
+                                 tiles_per_utt, a.KS, a.pad, kb_per_tap, BN, stages, total_tiles / 2, a.dilation > 1 ? a.dilation : 1));
+      SB_LAUNCH_OK();
+      return 0;
+    }
+  }
   KernFn kern = table[ia][il][ifast][ip];
   SB_OPT_IN_SMEM(attr_set[ia][il][ifast][ip], kern, 227 * 1024);
   const int grid = persist ? (total_tiles < ctas_per_sm * num_sms() ? total_tiles : ctas_per_sm * num_sms()) : total_tiles;

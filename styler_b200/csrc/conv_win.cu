@@ -177,9 +177,7 @@ __global__ void __launch_bounds__(kWThreads, 2) conv1d_win_kernel(const __grid_c
 }
 
 int win_mode() {   // STYLER_CONV_WIN=0 sends these shapes back to conv_tc.cu (A/B measurements)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("STYLER_CONV_WIN"); v = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
-  return v;
+  return tuning(TUNE_CONV_WIN);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

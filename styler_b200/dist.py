@@ -54,6 +54,18 @@ def gather_to_rank0(tensors, dst=0):
     return outs
 
 
+def gather_packed(packed, dst=0, bufs=None):
+    """One collective for a step's results: `packed` is the byte buffer of engine.packed_views (four fp32 mel tensors + int64
+    lengths back to back).  Returns the list of per-rank buffers on `dst` (engine.unpack_results reads them), None elsewhere."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [packed]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst and bufs is None:
+        bufs = [torch.empty_like(packed) for _ in range(world)]
+    dist.gather(packed, bufs if rank == dst else None, dst=dst)
+    return bufs if rank == dst else None
+
+
 class AsyncGather:
     """Gather of the per-rank mel tensors to rank 0 on a dedicated communication stream, so the NVLink transfer of
     step i overlaps the compute of step i+1 (the transfer is 84 MB per rank per step at config 3).  Receive buffers
@@ -63,7 +75,42 @@ class AsyncGather:
         self.device, self.dst = device, dst
         self.stream = torch.cuda.Stream(device=device)
         self._bufs = {}
+        self._done = {}
         self.result = None
+
+    def launch_packed(self, packed, slot=0):
+        """ONE gather per step: `packed` is Engine.last_packed (uint8: the four fp32 mel tensors and the int64 lengths back
+        to back, engine.packed_views).  `slot` names the (reused) buffer `packed` lives in -- e.g. the static outputs of CUDA
+        graph `slot`: call `before_reuse(slot)` before that buffer is written again.  On rank 0 `result` becomes the list
+        of per-rank byte buffers (engine.unpack_results turns each back into tensors)."""
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            self.result = [packed]
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            packed.record_stream(self.stream)
+            bufs = None
+            if rank == self.dst:
+                key = ("packed", slot, packed.numel())
+                if key not in self._bufs:
+                    self._bufs[key] = [torch.empty_like(packed) for _ in range(world)]
+                bufs = self._bufs[key]
+            gather_packed(packed, self.dst, bufs)
+            ev = self._done.get(slot)
+            if ev is None:
+                ev = self._done[slot] = torch.cuda.Event()
+            ev.record(self.stream)
+        self.result = bufs
+
+    def before_reuse(self, slot=0):
+        """Make the current stream wait for the last gather that read buffer `slot`."""
+        ev = self._done.get(slot)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def launch(self, tensors):
         if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -30,6 +30,31 @@ def sinusoid_table(n_position, d_hid=256):
     return torch.from_numpy(tab).float()
 
 
+N_MEL = 80
+
+
+def packed_nbytes(B, T):
+    return 4 * B * T * N_MEL * 4 + B * 8
+
+
+def packed_views(B, T, device, buf=None):
+    """One contiguous byte buffer holding a forward's results: fp32 [2B,T,80] (mel, mel_noisy) | fp32 [2B,T,80] (postnet,
+    postnet_noisy) | int64 [B] mel_len.  Returns ((buf, len_view), mel_view, post_view)."""
+    half = 2 * B * T * N_MEL * 4
+    if buf is None:
+        buf = torch.empty(packed_nbytes(B, T), device=device, dtype=torch.uint8)
+    mel = buf[:half].view(torch.float32).view(2 * B, T, N_MEL)
+    post = buf[half:2 * half].view(torch.float32).view(2 * B, T, N_MEL)
+    lens = buf[2 * half:2 * half + 8 * B].view(torch.int64)
+    return (buf, lens), mel, post
+
+
+def unpack_results(buf, B, T):
+    """Inverse of packed_views for a received buffer: (mel, mel_noisy, postnet, postnet_noisy, mel_len)."""
+    (_, lens), mel, post = packed_views(B, T, buf.device, buf)
+    return mel[:B], mel[B:], post[:B], post[B:], lens
+
+
 class _NS(dict):
     __getattr__ = dict.__getitem__
     __setattr__ = dict.__setitem__
@@ -48,11 +73,14 @@ class Engine:
         self.attn_impl = IMPL_SIMT if precision == "fp32" else IMPL_TC
         self._pos_cache = {}
         self.inter = {}
+        self.last_packed = None
         self.v_rowmajor = precision == "bf16"   # attention reads V row-major from the fused QKV buffer (MN-major B operand;
                                                # validated for kind::f16 only -- the fp32 modes keep the transposed-V layout)
         import os
         self.use_streams = os.environ.get("STYLER_NO_STREAMS", "0") != "1"   # four audio-encoder branches on side streams
         self._streams = None
+        self._branch_events = []
+        self._post = [None, None, None]
         self._pack({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
 
     # ------------------------------------------------------------------------------------------ packing
@@ -207,28 +235,49 @@ class Engine:
             c = ops.bilstm_layer(gx, whh, self.dt)
         return c
 
-    def audio_encoder(self, mel_target, p_idx, e_idx, mel_aug, mel_len, src_len, L, join=True):
+    def audio_encoder(self, mel_target, p_idx, e_idx, mel_aug, mel_len, src_len, L, join=True, classify=False):
         """modules.py:164-201 on the padded grid: conv stacks + GroupNorm + ReLU @Tr, Mel Calibrator, 2-layer BiLSTMs @L.
         The four style-factor branches are independent: each runs on its own CUDA stream so the latency-bound BiLSTM
-        recurrences (64 CTAs) overlap the other branches' convolutions instead of serialising."""
+        recurrences overlap the other branches' convolutions instead of serialising.
+        classify: also run the three augmentation classifiers (modules.py:319-321) at the tail of their branch's stream.  Their
+        posteriors are forward OUTPUTS that nothing downstream consumes, so the main stream only waits for the branch encodings
+        (`join_branches`, per-branch events) and picks the posteriors up at the very end of the forward (`join_audio_streams`)."""
         ins = (mel_target, p_idx, e_idx, mel_aug)
+        names = ("d", "p", "e", None)
+        self._post = [None, None, None]
         if not self.use_streams:
-            return [self._audio_branch(br, xin, mel_len, src_len, L) for br, xin in zip(self.w.branches, ins)]
+            outs = [self._audio_branch(br, xin, mel_len, src_len, L) for br, xin in zip(self.w.branches, ins)]
+            if classify:
+                self._post = [self._classifier(outs[i], self.w.cls[names[i]]) for i in range(3)]
+            return outs
         main = torch.cuda.current_stream(self.device)
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
         start = torch.cuda.Event()
         start.record(main)
-        outs = []
-        for st, br, xin in zip(self._streams, self.w.branches, ins):
+        outs, self._branch_events = [], []
+        for i, (st, br, xin) in enumerate(zip(self._streams, self.w.branches, ins)):
             st.wait_event(start)
             with torch.cuda.stream(st):
                 c = self._audio_branch(br, xin, mel_len, src_len, L)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                if classify and names[i] is not None:
+                    self._post[i] = self._classifier(c, self.w.cls[names[i]])
+                    self._post[i].record_stream(main)
             c.record_stream(main)
             outs.append(c)
+            self._branch_events.append(ev)
         if join:
             self.join_audio_streams()
         return outs
+
+    def join_branches(self):
+        """Main stream waits for the four branch ENCODINGS only (not for the classifiers queued behind them)."""
+        if self.use_streams and self._streams is not None:
+            main = torch.cuda.current_stream(self.device)
+            for ev in self._branch_events:
+                main.wait_event(ev)
 
     def join_audio_streams(self):
         if self.use_streams and self._streams is not None:
@@ -250,13 +299,14 @@ class Engine:
         return t if self.dt == torch.float32 else ops.cast(t, self.dt)
 
     # ------------------------------------------------------------------------------------------ decode (styler.py:29-37)
-    def decode(self, x, mel_lens):
-        """x [B,T,256] (activation dtype) -> (mel fp32 [B,T,80], mel_postnet fp32 [B,T,80])."""
+    def decode(self, x, mel_lens, mel_out=None, post_out=None):
+        """x [B,T,256] (activation dtype) -> (mel fp32 [B,T,80], mel_postnet fp32 [B,T,80]); the results are written into
+        mel_out / post_out when given (slices of the packed gather buffer)."""
         B, T, _ = x.shape
         h = ops.add(x, pos=self._pos("dec", T))
         for W in self.w.dec_layers:
             h = self.fft_block(h, mel_lens, W)
-        mel = torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
+        mel = mel_out if mel_out is not None else torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
         if self.dt == torch.float32:
             ops.conv1d(h, self.w.mel[0], self.w.mel[1], out=mel, impl=self.impl)
             mel_t = mel
@@ -267,7 +317,7 @@ class Engine:
         p = mel_t
         for j in range(4):
             p = ops.conv1d(p, self.w.postnet[j][0], self.w.postnet[j][1], pad=2, act=ACT_TANH, impl=self.impl)
-        post = torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
+        post = post_out if post_out is not None else torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
         ops.conv1d(p, self.w.postnet[4][0], self.w.postnet[4][1], pad=2, residual_f32=mel, out_f32=post, want_out=False,
                    impl=self.impl)
         return mel, post
@@ -283,7 +333,7 @@ class Engine:
         # the audio-encoder branches (side streams) overlap the text encoder and speaker projections (this stream)
         p_idx, e_idx = ops.quantize_index(p_norm), ops.quantize_index(e_input)                          # utils.py:417-429
         mel_t, mel_a = self._act(mel_target), self._act(mel_aug)
-        d_enc, p_enc, e_enc, n_enc = self.audio_encoder(mel_t, p_idx, e_idx, mel_a, mel_len, src_len, L, join=False)
+        d_enc, p_enc, e_enc, n_enc = self.audio_encoder(mel_t, p_idx, e_idx, mel_a, mel_len, src_len, L, join=False, classify=True)
         text = self.text_encoder(src_seq, src_len, out=enc[..., 0:256])
         neck = ops.conv1d(text, w.tld[0], w.tld[1], act=ACT_RELU, impl=self.impl)                      # [B,L,4]
         spk_in = self._act(speaker_embed).unsqueeze(0)                                                  # [1,B,512]
@@ -291,8 +341,8 @@ class Engine:
         spk = ops.conv1d(spk_in, w.sl[0], w.sl[1], act=ACT_RELU, impl=self.impl)[0]                     # [B,256]
         neck_up = ops.conv1d(neck, w.tlu[0], w.tlu[1], act=ACT_RELU, impl=self.impl)                    # [B,L,256]
         ops.add(None, rowvec=spk, out=enc[..., 512:768])
-        self.join_audio_streams()
-        post = tuple(self._classifier(x, w.cls[n]) for x, n in ((d_enc, "d"), (p_enc, "p"), (e_enc, "e")))
+        self.join_branches()
+        post = tuple(self._post)                       # produced on the side streams; valid after join_audio_streams() (end of forward)
         p_enc_sp = ops.add(p_enc, rowvec=spk_p)                                                         # modules.py:332
         d_up = self._mlp2(d_enc, w.mlp["duration"])
         p_up = self._mlp2(p_enc_sp, w.mlp["pitch"])
@@ -360,8 +410,15 @@ class Engine:
             T = int(max_mel_len) if max_mel_len else int(tot.max().item())     # the one host sync of the path
             x, x_noisy, _, p_pred, e_pred, out_len = self.variance_adapt(enc, log_d, T, None, None, p_target, e_target,
                                                                          d_control, p_control, e_control, duration=duration)
-        # styler.py:52,55: clean decode and noisy decode (x.detach() + noise_encoding) -- batched as one [2B] pass
-        mel2, post2 = self.decode(self._xx, out_len.repeat(2))
+        # styler.py:52,55: clean decode and noisy decode (x.detach() + noise_encoding) -- batched as one [2B] pass.
+        # The four mel tensors and the lengths land in ONE contiguous buffer [mel | mel_noisy | postnet | postnet_noisy | len]
+        # so that the data-parallel gather to rank 0 (dist.AsyncGather.launch_packed) is a single NCCL operation.
+        packed, mel_out, post_out = (None, None, None) if not self.w.postnet else packed_views(B, T, dev)
+        mel2, post2 = self.decode(self._xx, out_len.repeat(2), mel_out, post_out)
+        self.join_audio_streams()                      # the DAT posteriors (side streams) are outputs of this forward
+        if packed is not None:
+            packed[1].copy_(out_len)
+        self.last_packed = packed[0] if packed is not None else None
         self._xx = None
         mel, mel_n, post_mel, post_mel_n = mel2[:B], mel2[B:], post2[:B], post2[B:]
         ar = torch.arange(L, device=dev)

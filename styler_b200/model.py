@@ -423,6 +423,7 @@ class GraphedSTYLER:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = model(*self.static_args, **self.static_kwargs)
+        self.packed = eng.last_packed      # the captured results as one byte buffer (dist.AsyncGather.launch_packed)
 
     def __call__(self, *args, **kwargs):
         if self.model._engine is not self._eng:

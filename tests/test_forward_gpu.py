@@ -4,7 +4,8 @@ oracle/make_golden.py from the unmodified reference) and against the CPU oracle 
 Tolerances (tensor-normalised max error, |got-ref|.max() / |ref|.max(); north_star: 1e-3 relative on fp32 mels):
   fp32 mode (CUDA cores)      : 1e-4 everywhere
   tf32 mode (tcgen05 tf32)    : 1e-3 on the four mels, 5e-3 on predictor outputs
-  bf16 mode (tcgen05 bf16)    : 1e-2 on the mels, 3e-2 on predictor outputs (bf16 has an 8-bit mantissa)
+  bf16 mode (tcgen05 bf16)    : 1e-2 on the mels, 3e-2 on predictor outputs (bf16 has an 8-bit mantissa; SURVEY.md section 7);
+                                2e-2 on the stored inspection encodings (kept in bf16 storage, i.e. rounded once more)
 Integer outputs (mel_len, masks) are bit exact in every mode.
 """
 import os
@@ -18,8 +19,8 @@ from oracle import styler_oracle as so
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
-TOL = {"fp32": dict(mel=1e-4, pred=1e-4, post=1e-4), "tf32": dict(mel=1e-3, pred=5e-3, post=2e-3),
-       "bf16": dict(mel=1e-2, pred=3e-2, post=3e-2)}
+TOL = {"fp32": dict(mel=1e-4, pred=1e-4, post=1e-4, enc=1e-4), "tf32": dict(mel=1e-3, pred=5e-3, post=2e-3, enc=1e-3),
+       "bf16": dict(mel=1e-2, pred=3e-2, post=3e-2, enc=2e-2)}   # enc: inspection tensors, which live in bf16 STORAGE in bf16 mode
 
 
 def rel(got, ref):
@@ -66,7 +67,7 @@ def test_forward_vs_reference_golden(cuda, case, precision):
         errs[k] = rel(got[k], gold[k])
         assert errs[k] < tol["post"], (case, precision, k, errs[k])
     sm = model.style_modeling
-    assert rel(sm.text_encoding, gold["i_text_encoding"]) < tol["mel"]
+    assert rel(sm.text_encoding, gold["i_text_encoding"]) < tol["enc"]
     assert rel(sm.duration_encoding, gold["i_duration_encoding"]) < tol["pred"]
     assert rel(sm.noise_encoding, gold["i_noise_encoding"]) < tol["pred"]
     print("\n%s/%s " % (case, precision) + " ".join("%s=%.1e" % kv for kv in errs.items()))

@@ -121,9 +121,24 @@ outs = sdist.gather_to_rank0([mel, mine["mel_len"]])
 if rank == 0:
     assert outs[0].shape == (6, 4, 80) and outs[0][:3].eq(0).all() and outs[0][3:].eq(1).all()
     assert outs[1].tolist() == [0, 1, 2, 3, 4, 5]
-    print("GATHER_OK")
 else:
     assert outs[0] is None
+# one packed collective per step (engine.packed_views / dist.gather_packed): four mels + lengths in one byte buffer
+from styler_b200 import engine
+B, T = 3, 4
+(buf, lens), mel2, post2 = engine.packed_views(B, T, "cpu")
+assert buf.numel() == engine.packed_nbytes(B, T)
+mel2.fill_(float(rank)); post2.fill_(float(rank) + 0.5); mel2[B:] += 10; post2[B:] += 10
+lens.copy_(torch.arange(B) + 100 * rank)
+got = sdist.gather_packed(buf)
+if rank == 0:
+    for r in range(2):
+        mel, mel_n, post, post_n, ln = engine.unpack_results(got[r], B, T)
+        assert mel.shape == (B, T, 80) and mel.eq(r).all() and mel_n.eq(r + 10).all()
+        assert post.eq(r + 0.5).all() and post_n.eq(r + 10.5).all() and ln.tolist() == [100 * r, 100 * r + 1, 100 * r + 2]
+    print("GATHER_OK")
+else:
+    assert got is None
 """
 
 

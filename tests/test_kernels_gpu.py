@@ -173,6 +173,56 @@ def test_conv1d_tc_persistent(cuda, case):
     assert torch.equal(got, got2)
 
 
+PAIR_CASES = [
+    # CTA pairs (tcgen05 cta_group::2, M = 256 over two SMs): 256-wide N tiles, no residual.  Ragged T (partial last tile per
+    # utterance), odd tiles-per-utterance so a pair straddles two utterances, dilation, every activation.
+    # name,             B,  T,    Cin, N,    KS, kw
+    ("ffn1_k9_relu",    4,  1024, 256, 1024, 9, dict(act=1)),
+    ("postnet_k5_tanh", 6,  300,  512, 512,  5, dict(act=2)),
+    ("linear_256",      2,  700,  256, 256,  1, dict()),
+    ("k3_dil3_n512",    2,  1000, 128, 512,  3, dict(dil=3)),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_conv1d_tc_cta_pairs(cuda, case):
+    from styler_b200 import _lib
+    ops = _ops()
+    name, B, T, Cin, N, KS, kw = case
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(B, T, Cin, generator=g)
+    w = (torch.rand(KS, N, Cin, generator=g) * 2 - 1) / math.sqrt(Cin * KS)
+    bias = torch.randn(N, generator=g) * 0.1
+    dil = kw.get("dil", 1)
+    pad = dil * (KS - 1) // 2
+    y = F.conv1d(x.to(dtype).float().transpose(1, 2), w.to(dtype).float().permute(1, 2, 0).contiguous(), bias, padding=pad,
+                 dilation=dil).transpose(1, 2)
+    ref = ACTS[kw.get("act", 0)](y)
+    xd, wd, bd = x.to(cuda, dtype), w.to(cuda, dtype), bias.to(cuda)
+    args = dict(pad=pad, act=kw.get("act", 0), dilation=dil, impl=ops.IMPL_TC)
+    try:
+        _lib.set_tuning("TC_PERSIST", 0)
+        _lib.set_tuning("TC_BN", 256)                 # small problems would otherwise pick a narrower N tile
+        _lib.set_tuning("TC_2CTA", 0)
+        single = ops.conv1d(xd, wd, bd, **args)
+        _lib.set_tuning("TC_2CTA", 2)                 # wherever legal
+        n0 = _lib.launch_count()
+        pair = ops.conv1d(xd, wd, bd, **args)
+        pair2 = ops.conv1d(xd, wd, bd, **args)
+        torch.cuda.synchronize()
+        assert _lib.launch_count() == n0 + 2
+    finally:
+        _lib.set_tuning("TC_2CTA", -1)
+        _lib.set_tuning("TC_BN", -1)
+        _lib.set_tuning("TC_PERSIST", -1)
+    assert torch.isfinite(pair.float()).all()
+    for b in range(B):
+        assert rel_err(pair[b], ref[b]) < 1e-2, (name, b)
+    assert torch.equal(pair, pair2), "two launches must agree bitwise"
+    assert torch.equal(pair, single), "the pair form accumulates in the same order as the single-CTA form"
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("T", [128, 200, 520])
@@ -240,6 +290,52 @@ def test_attention_tc_edge_lengths_and_rising_max(cuda, dtype):
     tol = 1.5e-2 if dtype == torch.bfloat16 else 2e-2
     for b in range(B):
         assert rel_err(got[b], ref[b]) < tol, (b, int(lens[b]))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+def test_attention_tc_persistent_items(cuda, dtype):
+    """More (utterance, head, query-tile) work items than resident CTA slots: every CTA of the persistent attention kernel walks
+    several items, so the K/V ring, the S / P / PV hand-shakes, the Q refill and the O accumulators run across item
+    boundaries.  Ragged lengths give items with 1..8 key tiles next to each other (and a different tile count on either
+    side of most boundaries).  Checked per utterance against the CPU statement, and bitwise against the one-item-per-CTA
+    form of the same kernel (ATTN_PERSIST=0)."""
+    from styler_b200 import _lib
+    ops = _ops()
+    H, T = 4, 1024
+    B = 12 if dtype == torch.bfloat16 else 6            # 384 / 192 items > 296 / 148 slots
+    g = torch.Generator().manual_seed(23)
+    lens = torch.randint(1, T + 1, (B,), generator=g).to(torch.int64)
+    lens[0], lens[1], lens[2] = T, 1, 129
+    qk = torch.randn(B, T, 512, generator=g) * 0.7
+    v = torch.randn(B, T, 256, generator=g)
+    qkq, vq = qk.to(dtype).float(), v.to(dtype).float()
+    q = qkq[..., :256].view(B, T, H, 64).permute(0, 2, 1, 3)
+    k = qkq[..., 256:].view(B, T, H, 64).permute(0, 2, 1, 3)
+    vv = vq.view(B, T, H, 64).permute(0, 2, 1, 3)
+    sc = (q @ k.transpose(-1, -2)).masked_fill(so.mask_from_lengths(lens, T)[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vv).permute(0, 2, 1, 3).reshape(B, T, 256)
+
+    def run():
+        if dtype == torch.bfloat16:
+            return ops.attention(torch.cat([qk, v], dim=-1).to(cuda, dtype), None, lens.to(cuda), H, impl=ops.IMPL_TC)
+        vt = torch.zeros(B, 256, T, dtype=dtype)
+        vt[:, :, :T] = v.transpose(1, 2)
+        return ops.attention(qk.to(cuda, dtype), vt.to(cuda), lens.to(cuda), H, impl=ops.IMPL_TC)
+
+    try:
+        _lib.set_tuning("ATTN_PERSIST", 1)
+        got = run()
+        got2 = run()
+        _lib.set_tuning("ATTN_PERSIST", 0)
+        one = run()
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_tuning("ATTN_PERSIST", -1)
+    assert torch.isfinite(got.float()).all()
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 5e-3
+    for b in range(B):
+        assert rel_err(got[b], ref[b]) < tol, (b, int(lens[b]))
+    assert torch.equal(got, got2) and torch.equal(got, one)
 
 
 def test_embed_add_cast(cuda):
