@@ -464,6 +464,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every forward kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true", help="skip the tf32 and B=1 latency side measurements")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = the producing kernels store the mels straight into rank 0's IPC-mapped buffer over NVLink "
+                         "(fused compute + gather, dist.PeerGather); nccl = one packed NCCL gather per step")
     ap.add_argument("--workload", default="styler", choices=["styler", "vocoder", "fftblock", "stft"],
                     help="styler = BASELINE.json's headline metric, configs[2] (default); fftblock = configs[1]; stft = configs[3]; "
                          "vocoder = secondary HiFi-GAN line (all but styler: single GPU)")
@@ -518,27 +521,38 @@ def main():
     # so the gather (N > 1) or the D2H copies (e2e) of step i can still be reading graph k's outputs while step i+1 runs in
     # the other graph.
     use_graph = not args.no_graph
-    gatherer = sdist.AsyncGather(dev) if world > 1 else None
+    from styler_b200.engine import packed_nbytes
+    peer = world > 1 and args.gather == "peer"
+    gatherer = None
+    if world > 1:
+        gatherer = sdist.AsyncPeerGather(dev, packed_nbytes(B_PER_GPU, T)) if peer else sdist.AsyncGather(dev)
     for i in range(args.warmup):                    # eager warm-up: engine build, position tables, allocator pools
         model(*split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
     torch.cuda.synchronize()
     graphs = []
     if use_graph:
         a0, k0 = split(resident[0])
-        graphs = [GraphedSTYLER(model, a0, k0, warmup=1) for _ in range(2)]
+        # peer gather: graph k is captured with this rank's slice (slot k) of rank 0's receive region as the second destination
+        # of mel_linear / the last PostNet conv -- the NVLink stores are part of the captured kernels
+        graphs = [GraphedSTYLER(model, a0, k0, warmup=1, result_mirror=gatherer.buffer(k) if peer else None) for k in range(2)]
 
     def step(bt, slot):
         a, kw = split(bt)
+        if peer:
+            gatherer.begin(slot)                     # flow control: rank 0 has consumed the previous contents of this slot
+        elif gatherer is not None and use_graph:
+            gatherer.before_reuse(slot)              # the previous gather out of this graph's static outputs has drained
         if use_graph:
-            if gatherer is not None:
-                gatherer.before_reuse(slot)          # the previous gather out of this graph's static outputs has drained
             out = graphs[slot](*a, **kw)
             packed = graphs[slot].packed
         else:
+            eng = model._engine_for()
+            eng.result_mirror = gatherer.buffer(slot) if peer else None
             out = model(*a, **kw)
-            packed = model._engine.last_packed
-        if gatherer is not None:   # ONE NCCL gather (4 mels + lengths, one byte buffer) to rank 0 on the comm stream
-            gatherer.launch_packed(packed, slot)
+            eng.result_mirror = None
+            packed = eng.last_packed
+        if gatherer is not None:   # nccl: ONE gather (4 mels + lengths, one byte buffer) on the comm stream; peer: publish the
+            gatherer.launch_packed(packed, slot)     # completion counter (rank 0: wait for all ranks, then release the slot)
         return out
 
     def barrier():
@@ -629,7 +643,6 @@ def main():
     # Two user streams alternate (each with its own graph / pinned result buffers): step i's H2D / D2H copies overlap step
     # i+-1's kernels, as a serving loop would drive the public API.  Every step does its own H2D of all inputs and the D2H of
     # ALL FOUR mel tensors + lengths (one packed buffer) inside the timed region.
-    from styler_b200.engine import packed_nbytes
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
     d2h = [torch.empty(packed_nbytes(B_PER_GPU, T), dtype=torch.uint8).pin_memory() for _ in range(2)]
 
@@ -720,6 +733,9 @@ def main():
                                                     "wall clock per call incl. synchronize; eager has one host read of max(mel_len)"}
         del g1, m1
 
+    if peer:
+        torch.cuda.synchronize()
+        gatherer.close()
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -740,8 +756,11 @@ def main():
                                % (B_PER_GPU, L, T, FRAMES, T, args.precision),
                    "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world,
                    "launch": "CUDA-graph replay of the forward (2 alternating graphs)" if use_graph else "eager kernel launches",
-                   "gather": "one packed NCCL gather per step (4 fp32 mels + lengths, %d bytes/rank), inside the timed events"
-                             % packed_nbytes(B_PER_GPU, T) if world > 1 else "none (N=1)",
+                   "gather": ("none (N=1)" if world == 1 else
+                              ("fused compute+gather: mel_linear / last PostNet conv store into rank 0's IPC-mapped buffer over NVLink "
+                               "(%d bytes/rank/step), flag protocol; inside the timed events" if peer else
+                               "one packed NCCL gather per step (4 fp32 mels + lengths, %d bytes/rank), inside the timed events")
+                              % packed_nbytes(B_PER_GPU, T)),
                    "l2": "inputs rotate over %d resident batches (> L2); per-step activations >> L2; no explicit flush" % NBUF},
         "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_secs / args.steps,

@@ -69,6 +69,9 @@ typedef struct {
   int32_t residual_inv_lrelu;                            /* 1: `residual` holds lrelu(r) (slope act_slope); r is recovered as
                                                             (v < 0 ? v / act_slope : v) before the add, so a HiFi-GAN residual
                                                             chain can be stored in activated form only */
+  float* out2_f32;                                       /* optional SECOND fp32 destination, same strides as out_f32 (requires
+                                                            out_f32): e.g. the slice of rank 0's peer-mapped gather buffer, so
+                                                            the result crosses NVLink from the producing epilogue */
 } styler_conv1d_args;
 int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream);
 
@@ -140,8 +143,10 @@ int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, co
                               int32_t Tr, int32_t L, int32_t C, int32_t dtype, void* stream);
 
 /* ---- One layer of a bidirectional LSTM over the padded grid (modules.py:179-182; nn.LSTM, gates i,f,g,o).
- * gx: fp32 [B][L][8H] = x @ [W_ih_fwd ; W_ih_rev]^T + (b_ih+b_hh) (produced by styler_conv1d_fwd);
- * whh: fp32 [2][4H][H]; out: [B][L][2H] (fwd | rev), dtype. */
+ * gx: fp32 [B][L][2][H][4] = x @ W_ih^T + (b_ih + b_hh) in QUAD order: direction (fwd, rev), hidden unit, gate (i,f,g,o)
+ * innermost -- i.e. the rows of [W_ih_fwd ; W_ih_rev] permuted from PyTorch's [dir][gate][unit] to [dir][unit][gate] before the
+ * projection (produced by styler_conv1d_fwd; 16-byte aligned);
+ * whh: fp32 [2][4H][H] in PyTorch row order; out: [B][L][2H] (fwd | rev), dtype. */
 int styler_bilstm_layer_fwd(const float* gx, const float* whh, void* out, int64_t o_bstride, int32_t o_ld,
                             int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
 
@@ -202,6 +207,20 @@ int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, const float* me
 /* ---- f0_normalization / speaker_normalization (utils.py:387-409) over a padded batch of log-f0 contours [B][T]
  * (unvoiced frames marked <= -1e10 keep their value; rows with undefined statistics and frames >= lens[b] are zero). */
 int styler_f0_norm_fwd(const float* f0, const int64_t* lens, float* out, int32_t B, int32_t T, void* stream);
+
+/* ---- Peer memory for the fused compute + gather (one process per GPU; replaces nn.DataParallel's gather, train.py:33):
+ * peer_alloc: cudaMalloc'ed, zeroed region + its 64-byte CUDA IPC handle; peer_open maps another process's region (NVLink
+ * P2P, peer access enabled lazily); the fp32 outputs of the last convolutions are then written straight into the mapped
+ * slice (out_f32 / out2_f32 of styler_conv1d_fwd).  peer_signal enqueues a one-thread kernel that publishes `value` at
+ * `flag` (device or peer memory) with system-scope release semantics after everything enqueued before it on `stream`;
+ * peer_wait enqueues a kernel that spins until flags[i * stride] >= value for all i < n (system-scope acquire, ~10 s
+ * watchdog that traps instead of hanging). */
+int styler_peer_alloc(int64_t bytes, void** dptr, void* handle64);
+int styler_peer_open(const void* handle64, void** dptr);
+int styler_peer_close(void* dptr);
+int styler_peer_free(void* dptr);
+int styler_peer_signal(void* flag, uint64_t value, void* stream);
+int styler_peer_wait(const void* flags, int32_t n, int64_t stride, uint64_t value, void* stream);
 
 /* ---- A/B switches of the library (each also read once from the environment as STYLER_<NAME>): "TC_2CTA" (CTA pairs /
  * tcgen05 cta_group::2 for the big bf16 convolutions: 0 off, 1 where it pays, 2 wherever legal), "TC_PERSIST", "CONV_WIN",

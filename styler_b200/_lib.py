@@ -33,6 +33,7 @@ class Conv1dArgs(ctypes.Structure):
         ("vt", c_vp), ("vt_col0", c_i32), ("vt_bstride", c_i64), ("vt_ld", c_i32),
         ("dtype", c_i32), ("impl", c_i32),
         ("dilation", c_i32), ("act_slope", c_f32), ("residual_inv_lrelu", c_i32),
+        ("out2_f32", c_vp),
     ]
 
 
@@ -83,6 +84,12 @@ _SIGNATURES = {
     "styler_f0_norm_fwd": [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp],
     "styler_debug_set_phase_buffer": [c_vp, c_i32],
     "styler_set_tuning": [ctypes.c_char_p, c_i32],
+    "styler_peer_alloc": [c_i64, ctypes.POINTER(c_vp), c_vp],
+    "styler_peer_open": [c_vp, ctypes.POINTER(c_vp)],
+    "styler_peer_close": [c_vp],
+    "styler_peer_free": [c_vp],
+    "styler_peer_signal": [c_vp, ctypes.c_uint64, c_vp],
+    "styler_peer_wait": [c_vp, c_i32, c_i64, ctypes.c_uint64, c_vp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["styler_version", "styler_last_error", "styler_launch_count"])
 

@@ -33,9 +33,9 @@ struct TuneDef { const char* name; int dflt, lo, hi; };
 // TC_2CTA: CTA pairs for the big bf16 convs (0 off | 1 where it pays | 2 wherever legal: tests);  TC_PERSIST: persistent conv
 // form (0 | 1 two CTAs/SM | 2 also one CTA/SM);  CONV_WIN: window kernel for <= 64-channel convs;  TC_BN / TC_SMEM_KB: tile and
 // pipeline-depth overrides;  PDL: programmatic dependent launch (off: measured 8.71 ms/step with it vs 8.07 without);
-// ATTN_PERSIST: persistent attention CTAs (0 | 1)
+// ATTN_PERSIST: persistent attention CTAs (0 | 1);  TC_WIDE: full-width N tile (two MMAs per k-step) for 256 < N <= 512
 const TuneDef kTune[TUNE_COUNT] = {{"TC_2CTA", 1, 0, 2}, {"TC_PERSIST", 1, 0, 2}, {"CONV_WIN", 1, 0, 1}, {"TC_BN", 0, 0, 256},
-                                   {"TC_SMEM_KB", 110, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}};
+                                   {"TC_SMEM_KB", 110, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}, {"TC_WIDE", 1, 0, 1}};
 std::atomic<int> g_tune[TUNE_COUNT];          // 0 = not resolved yet, else value + 1
 }  // namespace
 

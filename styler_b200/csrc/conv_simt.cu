@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(styler_conv1d_args a, 
         if (a.out != nullptr)
           DT<T>::st(static_cast<T*>(a.out) + b * a.o_bstride + static_cast<long long>(t) * a.o_ld + n, v);
         if (a.out_f32 != nullptr) a.out_f32[b * a.of_bstride + static_cast<long long>(t) * a.of_ld + n] = v;
+    if (a.out2_f32 != nullptr) a.out2_f32[b * a.of_bstride + static_cast<long long>(t) * a.of_ld + n] = v;
+        if (a.out2_f32 != nullptr) a.out2_f32[b * a.of_bstride + static_cast<long long>(t) * a.of_ld + n] = v;
       }
     }
   }
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(kSmallT) conv1d_smalln_kernel(styler_conv1d_ar
     if (masked) v = 0.f;
     if (a.out != nullptr) DT<T>::st(static_cast<T*>(a.out) + b * a.o_bstride + static_cast<long long>(t) * a.o_ld + n, v);
     if (a.out_f32 != nullptr) a.out_f32[b * a.of_bstride + static_cast<long long>(t) * a.of_ld + n] = v;
+    if (a.out2_f32 != nullptr) a.out2_f32[b * a.of_bstride + static_cast<long long>(t) * a.of_ld + n] = v;
   }
 }
 

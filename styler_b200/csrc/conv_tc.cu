@@ -51,6 +51,7 @@ struct EpiParams {
   const float* dot_w; float dot_b; float* dot_out;
   void* out; long long o_bstride; int o_ld;
   float* out_f32; long long of_bstride; int of_ld;
+  float* out2_f32;            // optional second fp32 destination (same strides): peer-mapped gather slice
   void* vt; int vt_col0; long long vt_bstride; int vt_ld;
 };
 
@@ -151,8 +152,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;        // [2] epilogue -> MMA (persistent only)
   uint64_t* res_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
-  float* s_par = reinterpret_cast<float*>(tail + 256);                          // [4][256]: bias, gamma, beta, dot_w
-  float* s_x = s_par + 1024;                                                    // [256 threads][4]: LN / dot exchange
+  const int pstr = BN > 256 ? 512 : 256;                                        // per-column parameter vectors: [4][pstr]
+  float* s_par = reinterpret_cast<float*>(tail + 256);                          // bias, gamma, beta, dot_w
+  float* s_x = s_par + 4 * pstr;                                                // [256 threads][4]: LN / dot exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = ep.dbg != nullptr ? ep.dbg + static_cast<long long>(blockIdx.x) * 8 : nullptr;
@@ -205,6 +207,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
             mbar_arrive_expect_tx(&full[s], stage_bytes);
             tma_load_3d(sa, &tmA, &full[s], kc, t0 + tap * dil - pad, b);
             tma_load_3d(sa + kAStageBytes, &tmB, &full[s], kc, n0, tap);
+            if (BN > 256)        // wide tile: a TMA box has at most 256 rows, the weight tile arrives as two boxes of BN/2 rows
+              tma_load_3d(sa + kAStageBytes + (BN / 2) * 128, &tmB, &full[s], kc, n0 + BN / 2, tap);
           }
         }
         if (!PERSIST && (FAST ? ep.residual != nullptr : ep.stage_res != 0)) {
@@ -219,7 +223,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {
-      const uint32_t idesc = umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, CG2 ? 2 * kBM : kBM, BN);
+      // WIDE tile (256 < BN <= 512, e.g. the 320-channel audio-encoder convs): one A stage feeds TWO MMAs of BN/2 columns each,
+      // so the activations are pulled from L2 once per 128 x BN outputs (these convs are bound by operand bytes, not by the pipe)
+      const int mma_n = BN > 256 ? BN / 2 : BN;
+      const uint32_t idesc = umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, CG2 ? 2 * kBM : kBM, mma_n);
       int g = 0, it = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
         const int ab = PERSIST ? (it & 1) : 0;
@@ -241,9 +248,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
             if constexpr (CG2)
               umma_ss_2cta_f16(acc, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
                                (kb | k) != 0 ? 1u : 0u);
-            else
+            else {
               umma_ss<kTf32>(acc, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
                              (kb | k) != 0 ? 1u : 0u);
+              if (mma_n != BN)     // second half of the wide tile: weight rows mma_n.., accumulator columns mma_n..
+                umma_ss<kTf32>(acc + mma_n, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + mma_n * 128 + k * 32),
+                               idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if constexpr (CG2) umma_commit_2cta(&empty[s], 3); else umma_commit(&empty[s]);   // pair: frees the stage in BOTH CTAs
         }
@@ -298,6 +309,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     float* of_row = !FAST && ep.out_f32 != nullptr
                         ? ep.out_f32 + b * ep.of_bstride + static_cast<long long>(t) * ep.of_ld + n0
                         : nullptr;
+    float* of2_row = !FAST && ep.out2_f32 != nullptr
+                         ? ep.out2_f32 + b * ep.of_bstride + static_cast<long long>(t) * ep.of_ld + n0
+                         : nullptr;
     T* vt_base = to_vt ? static_cast<T*>(ep.vt) + b * ep.vt_bstride +
                              static_cast<long long>(n0 - ep.vt_col0) * ep.vt_ld + t
                        : nullptr;
@@ -308,16 +322,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       const int te = threadIdx.x - 64;
       for (int i = te; i < BN; i += 256) {
         s_par[i] = ep.bias != nullptr ? ep.bias[n0 + i] : 0.f;
-        s_par[256 + i] = has_ln ? ep.ln_gamma[n0 + i] : 1.f;
-        s_par[512 + i] = has_ln ? ep.ln_beta[n0 + i] : 0.f;
-        s_par[768 + i] = ep.dot_w != nullptr ? ep.dot_w[n0 + i] : 0.f;
+        s_par[pstr + i] = has_ln ? ep.ln_gamma[n0 + i] : 1.f;
+        s_par[2 * pstr + i] = has_ln ? ep.ln_beta[n0 + i] : 0.f;
+        s_par[3 * pstr + i] = ep.dot_w != nullptr ? ep.dot_w[n0 + i] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const float* s_bias = s_par;
-    const float* s_gamma = s_par + 256;
-    const float* s_beta = s_par + 512;
-    const float* s_dot = s_par + 768;
+    const float* s_gamma = s_par + pstr;
+    const float* s_beta = s_par + 2 * pstr;
+    const float* s_dot = s_par + 3 * pstr;
     auto ld16s = [](const float* p, float (&o)[16]) {   // 16 consecutive smem floats as 4 x LDS.128 (p is 64-byte aligned)
 #pragma unroll
       for (int g4 = 0; g4 < 4; ++g4) {
@@ -492,6 +506,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
             for (int i = 0; i < 16; i += 4)
               *reinterpret_cast<float4*>(of_row + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
+          if (of2_row != nullptr) {   // e.g. rank 0's receive buffer over NVLink: the gather is fused into this epilogue
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(of2_row + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
         }
       }
     };
@@ -586,6 +605,11 @@ int cg2_mode() { return tuning(TUNE_TC_2CTA); }
 
 int pick_bn(const styler_conv1d_args& a, int m_tiles) {
   if (a.ln_gamma != nullptr || a.dot_w != nullptr) return (a.N <= 256 && a.N % 16 == 0) ? a.N : 0;
+  const int es0 = a.dtype == STYLER_BF16 ? 2 : 4;
+  // full-width tile for 256 < N <= 512 that is not a multiple of 256 (the 320-channel convs): see the MMA issuer
+  if (tuning(TUNE_TC_WIDE) != 0 && es0 == 2 && a.N > 256 && a.N <= 512 && a.N % 256 != 0 && a.N % 32 == 0 && (a.N * es0) % 128 == 0 &&
+      a.out != nullptr && a.vt == nullptr && a.out_f32 == nullptr && m_tiles >= num_sms())
+    return a.N;
   const int forced = tuning(TUNE_TC_BN);   // tuning override: STYLER_TC_BN
   if (forced > 0 && forced % 16 == 0 && forced <= 256 && a.N % forced == 0 && (a.vt == nullptr || a.vt_col0 % forced == 0))
     return forced;
@@ -643,11 +667,13 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   // of M tiles, and enough tiles that pairing costs no occupancy
   // (LayerNorm rows, N = 256, included: their B tile is 2/3 of the operand bytes and their 48 KB stages only fit twice)
   const bool cg2 = cg2_mode() != 0 && es == 2 && !persist && fast_like && BN == 256 && (m_tiles % 2) == 0 &&
-                   (cg2_mode() == 2 || (num_kb >= 4 && total_tiles >= 2 * num_sms()));
+                   (cg2_mode() == 2 || (num_kb >= 8 && total_tiles >= 2 * num_sms()));   // (K = 256 out-proj measured slower paired)
   const int stage_bytes = kAStageBytes + (cg2 ? BN / 2 : BN) * 128;
   const int staging_bytes = persist ? BN * es * kBM : 0;
-  const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/ + 4096 /*exchange*/;
-  int stages = ((persist ? (ctas_per_sm == 2 ? 113 : 226) * 1024 - staging_bytes - fixed_bytes : smem_budget_bytes())) / stage_bytes;
+  const bool wide = BN > 256;
+  const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + (wide ? 8192 : 4096) /*params*/ + 4096 /*exchange*/;
+  int stages = ((persist ? (ctas_per_sm == 2 ? 113 : 226) * 1024 - staging_bytes - fixed_bytes
+                         : (wide ? 200 * 1024 : smem_budget_bytes()))) / stage_bytes;
   if (stages > (persist ? 4 : 8)) stages = persist ? 4 : 8;
   if (!persist && stages > num_kb) stages = num_kb;
   if (stages < 2) stages = (persist || num_kb >= 2) ? 2 : 1;
@@ -666,7 +692,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(a.Cin), static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.KS)};
     const uint64_t strides[2] = {static_cast<uint64_t>(a.Cin) * es, static_cast<uint64_t>(a.Cin) * a.N * es};
-    const uint32_t box[3] = {static_cast<uint32_t>(bke), static_cast<uint32_t>(cg2 ? BN / 2 : BN), 1};
+    const uint32_t box[3] = {static_cast<uint32_t>(bke), static_cast<uint32_t>((cg2 || BN > 256) ? BN / 2 : BN), 1};
     int rc = make_tmap(&tmB, a.w, es == 2 ? 1 : 0, 3, dims, strides, box);
     if (rc != 0) return rc;
   }
@@ -703,7 +729,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   ep.lens = a.lens;
   ep.dot_w = a.dot_w; ep.dot_b = a.dot_b; ep.dot_out = a.dot_out;
   ep.out = a.out; ep.o_bstride = a.o_bstride; ep.o_ld = a.o_ld;
-  ep.out_f32 = a.out_f32; ep.of_bstride = a.of_bstride; ep.of_ld = a.of_ld;
+  ep.out_f32 = a.out_f32; ep.of_bstride = a.of_bstride; ep.of_ld = a.of_ld; ep.out2_f32 = a.out2_f32;
   ep.vt = a.vt; ep.vt_col0 = a.vt_col0; ep.vt_bstride = a.vt_bstride; ep.vt_ld = a.vt_ld;
 
   using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, EpiParams, int, int, int, int, int, int, int, int, int, int);
@@ -765,6 +791,7 @@ bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why) {
     return fail("out not 16-byte aligned/strided");
   if (a.out_f32 != nullptr && (!aligned16(a.out_f32) || (a.of_ld % 4) != 0 || (a.of_bstride % 4) != 0))
     return fail("out_f32 not 16-byte aligned/strided");
+  if (a.out2_f32 != nullptr && (a.out_f32 == nullptr || !aligned16(a.out2_f32))) return fail("out2_f32 needs out_f32 and 16-byte alignment");
   const int res_es = a.residual_is_f32 ? 4 : es;
   if (a.residual != nullptr && (!aligned16(a.residual) || (static_cast<int64_t>(a.r_ld) * res_es) % 16 != 0 || (a.r_bstride * res_es) % 16 != 0))
     return fail("residual not 16-byte aligned/strided");

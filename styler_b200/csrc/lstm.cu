@@ -1,7 +1,7 @@
 // One layer of a bidirectional LSTM over the padded, un-packed [B, L] grid (modules.py:179-182 of the reference
 // runs nn.LSTM on padded tensors, so the reverse direction starts inside the padding -- reproduced here).
 // The input projection x@W_ih^T + b_ih + b_hh for all steps and both directions is a tensor-core GEMM done by
-// styler_conv1d_fwd (gx, fp32 [B][L][8H]); this kernel is the latency-bound recurrence (128 dependent steps).
+// styler_conv1d_fwd (gx, fp32 [B][L][2][H][4]); this kernel is the latency-bound recurrence (128 dependent steps).
 //
 // Round-2 form (the round-1 kernel spent 1650 clk per step: 2 utterances per CTA = 160 dependent-issue FFMA per thread
 // on the rt=2 FMA pipe, plus two block barriers and a smem gate exchange per step; ncu: profiles/ncu_bilstm_r2.md):
@@ -13,9 +13,12 @@
 //   * each thread applies the activation of ITS gate (the quad's four MUFU ops run in parallel), the activated values are
 //     shuffled, every thread of the quad keeps c redundantly, the g == 0 thread publishes h;
 //   * h is double-buffered in shared memory -> ONE block barrier per step;
-//   * gx is prefetched four steps ahead (it comes from L2 / HBM, 600-1000 clk away; a step takes ~400).
+//   * gx is streamed into shared memory by bulk async copies (cp.async.bulk + mbarrier), three 8-step chunks ahead; it is
+//     stored by the projection GEMM in QUAD order [B][L][2 dirs][H units][4 gates] (the rows of W_ih are permuted at pack
+//     time), so element t of a row belongs to thread t: contiguous copies, conflict-free reads.
 // Gate order i, f, g, o (PyTorch).  State and gates are fp32 regardless of the activation dtype.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace sb {
 namespace {
@@ -26,14 +29,19 @@ __device__ __forceinline__ float tanh_fast(float x) {   // MUFU.TANH, rel. error
   return y;
 }
 
+constexpr int kChunk = 8;      // steps of gx per bulk copy group
+constexpr int kBufs = 4;       // chunks in flight / in use: gx is fetched 3 chunks = 24 steps (~10 k clk) ahead of its use
+
 template <typename T, int H>
 __global__ void __launch_bounds__(4 * H) bilstm_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
                                                        T* __restrict__ out, long long o_bs, int o_ld, int L) {
   constexpr int G = 4 * H;
   const int b = blockIdx.x, dir = blockIdx.y;
   const int t = threadIdx.x, gate = t & 3, k = t >> 2;
-  const int row = gate * H + k;                             // PyTorch row of this (gate, unit)
+  const int row = gate * H + k;                             // PyTorch row of this (gate, unit) in W_hh
   __shared__ __align__(16) float hs[2][H];
+  __shared__ __align__(128) float gbuf[kBufs][kChunk][G];   // gx chunks, element t of a row belongs to thread t (quad order)
+  __shared__ __align__(8) uint64_t gbar[kBufs];
   float2 w2[H / 2];
   {
     const float2* wrow = reinterpret_cast<const float2*>(whh + (static_cast<long long>(dir) * G + row) * H);
@@ -41,28 +49,38 @@ __global__ void __launch_bounds__(4 * H) bilstm_kernel(const float* __restrict__
     for (int i = 0; i < H / 2; ++i) w2[i] = wrow[i];
   }
   if (t < H) hs[0][t] = 0.f;
-  float c = 0.f;
-  const float* gxb = gx + static_cast<long long>(b) * L * (2 * G) + dir * G + row;
-  auto gx_at = [&](int step) -> float {
-    if (step >= L) return 0.f;
-    const int tt = dir ? L - 1 - step : step;
-    return __ldg(gxb + static_cast<long long>(tt) * (2 * G));
-  };
-  // gx is read from L2 / HBM (600-1000 clk away) while a step takes ~400 clk: keep kPF steps of it in flight
-  constexpr int kPF = 4;
-  float gq[kPF];
-#pragma unroll
-  for (int u = 0; u < kPF; ++u) gq[u] = gx_at(u);
-  T* ob = out + b * o_bs + dir * H + k;
+  if (t == 0) {
+    for (int i = 0; i < kBufs; ++i) mbar_init(&gbar[i], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
+  // gx comes from HBM / L2 (ncu on the register-prefetch version: 34 % of all stall samples on the first use of the loaded
+  // value): one thread streams it into shared memory with bulk async copies (one 4H-float row per step), kBufs - 1 chunks ahead
+  const float* gxb = gx + static_cast<long long>(b) * L * (2 * G) + dir * G;
+  const int n_chunks = (L + kChunk - 1) / kChunk;
+  auto fetch = [&](int c) {                                 // thread 0 only
+    const int rows = min(kChunk, L - c * kChunk);
+    uint64_t* bar = &gbar[c % kBufs];
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(rows * G * sizeof(float)));
+    for (int u = 0; u < rows; ++u) {
+      const int step = c * kChunk + u;
+      const int tt = dir ? L - 1 - step : step;
+      bulk_load_1d(&gbuf[c % kBufs][u][0], gxb + static_cast<long long>(tt) * (2 * G), G * sizeof(float), bar);
+    }
+  };
+  if (t == 0)
+    for (int c = 0; c < kBufs - 1 && c < n_chunks; ++c) fetch(c);
+  float c_state = 0.f;
+  T* ob = out + b * o_bs + dir * H + k;
   const int qbase = (threadIdx.x & 31) & ~3;                // first lane of this quad
-  for (int step0 = 0; step0 < L; step0 += kPF) {
-#pragma unroll
-    for (int u = 0; u < kPF; ++u) {
-      const int step = step0 + u;
-      if (step >= L) break;                                 // block-uniform
-      const float gcur = gq[u];
-      gq[u] = gx_at(step + kPF);
+  for (int c = 0; c < n_chunks; ++c) {
+    // every thread passed the barrier that ended chunk c - 1, so its buffer (= that of chunk c + kBufs - 1) is free again
+    if (t == 0 && c + kBufs - 1 < n_chunks) fetch(c + kBufs - 1);
+    mbar_wait(&gbar[c % kBufs], (c / kBufs) & 1);
+    const int rows = min(kChunk, L - c * kChunk);
+    for (int u = 0; u < rows; ++u) {
+      const int step = c * kChunk + u;
+      const float gcur = gbuf[c % kBufs][u][t];
       const float4* h4 = reinterpret_cast<const float4*>(hs[step & 1]);
       float2 a0 = make_float2(gcur, 0.f), a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f), a3 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -88,10 +106,10 @@ __global__ void __launch_bounds__(4 * H) bilstm_kernel(const float* __restrict__
       const float f_ = __shfl_sync(0xffffffffu, act, qbase + 1);
       const float g_ = __shfl_sync(0xffffffffu, act, qbase + 2);
       const float o_ = __shfl_sync(0xffffffffu, act, qbase + 3);
-      c = fmaf(f_, c, i_ * g_);
+      c_state = fmaf(f_, c_state, i_ * g_);
       float h;
-      if constexpr (sizeof(T) == 2) h = o_ * tanh_fast(c);
-      else h = o_ * tanhf(c);
+      if constexpr (sizeof(T) == 2) h = o_ * tanh_fast(c_state);
+      else h = o_ * tanhf(c_state);
       if (gate == 0) {
         hs[(step + 1) & 1][k] = h;
         const int tt = dir ? L - 1 - step : step;
@@ -120,6 +138,7 @@ extern "C" int styler_bilstm_layer_fwd(const float* gx, const float* whh, void* 
   SB_REQUIRE(B > 0 && L > 0, "bilstm: bad shape");
   SB_REQUIRE(H == 64 || H == 80, "bilstm: hidden size %d not instantiated (64, 80)", H);
   SB_REQUIRE((reinterpret_cast<uintptr_t>(whh) & 7) == 0, "bilstm: W_hh must be 8-byte aligned");
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(gx) & 15) == 0, "bilstm: gx must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SB_DISPATCH_DTYPE(dtype, T, {
     if (H == 64) return launch<T, 64>(gx, whh, out, o_bstride, o_ld, B, L, s);

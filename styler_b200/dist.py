@@ -139,3 +139,201 @@ class AsyncGather:
     def wait(self):
         torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return self.result
+
+
+class _RawDeviceMemory:
+    """A device allocation that did not come from torch (styler_peer_alloc / styler_peer_open) exposed through the CUDA array
+    interface, so `torch.as_tensor` can wrap it without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = int(ptr), int(nbytes)
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+
+class PeerGather:
+    """Fused compute + gather over NVLink peer memory (SURVEY.md 8(e) phase 2), the replacement for nn.DataParallel's gather
+    (train.py:33, synthesize.py:62 of the reference) when every GPU has its own process.
+
+    Rank 0 owns a receive region [world][slots][packed_nbytes]; every other rank maps it (CUDA IPC) and hands ITS slice to the
+    engine as `result_mirror`: mel_linear and the last PostNet convolution then store their fp32 results straight into rank
+    0's memory from their epilogues -- the mel tensors cross NVLink while the tensor-core kernel that computes them is still
+    running, there is no staging copy and no collective.  Completion and buffer reuse are two counters per (rank, slot):
+      ready[r][slot]  (in rank 0's memory, written by rank r after its forward, system-scope release)
+      ack[slot]       (in rank r's memory, written by rank 0 once it has consumed that slot)
+    `slots` = 2 lets step i+1 run while rank 0 still reads step i.
+
+    Per step, on every rank:      buf = pg.begin(slot)    # waits (on the stream) until rank 0 has released the slot
+                                  ... forward with engine.result_mirror = pg.buffer(slot) ...
+                                  pg.commit(slot)         # publishes ready[rank][slot]
+    and on rank 0 additionally:   bufs = pg.collect(slot) # stream-waits for every rank; list of per-rank byte buffers
+                                  ... consume ...         # engine.unpack_results(bufs[r], B, T)
+                                  pg.release(slot)        # lets the ranks overwrite the slot
+    """
+
+    def __init__(self, device, nbytes, slots=2, dst=0):
+        import ctypes
+        from . import _lib
+        assert dist.is_initialized(), "PeerGather needs an initialised process group (handle exchange)"
+        self._lib, self._ct = _lib, ctypes
+        self.device, self.nbytes, self.slots, self.dst = torch.device(device), int(nbytes), int(slots), dst
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.stride = (self.nbytes + 255) // 256 * 256
+        self.uses = [0] * self.slots
+        self._own, self._mapped, self._keep = [], [], []
+        with torch.cuda.device(self.device):
+            # ack flags live on every rank (rank 0 writes them remotely); the big region and the ready flags on rank 0
+            ack_ptr, ack_h = self._alloc(256)
+            if self.rank == dst:
+                recv_ptr, recv_h = self._alloc(self.world * self.slots * self.stride)
+                ready_ptr, ready_h = self._alloc(256 * self.world)          # ready[r][slot] at byte 256 r + 8 slot
+            else:
+                recv_h = ready_h = None
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (recv_h, ready_h, ack_h))
+            if self.rank == dst:
+                self.recv_ptr, self.ready_ptr = recv_ptr, ready_ptr
+                self.ack_remote = [None if r == dst else self._open(gathered[r][2]) for r in range(self.world)]
+            else:
+                self.recv_ptr, self.ready_ptr = self._open(gathered[dst][0]), self._open(gathered[dst][1])
+            self.ack_ptr = ack_ptr
+            dist.barrier()                                                   # everybody has mapped everything
+
+    # -- raw memory helpers --------------------------------------------------------------------------------------------
+    def _alloc(self, nbytes):
+        ct = self._ct
+        p, h = ct.c_void_p(), (ct.c_ubyte * 64)()
+        self._lib.check(self._lib.lib().styler_peer_alloc(int(nbytes), ct.byref(p), h), "peer_alloc")
+        self._own.append(p.value)
+        return p.value, bytes(h)
+
+    def _open(self, handle):
+        ct = self._ct
+        p = ct.c_void_p()
+        buf = (ct.c_ubyte * 64).from_buffer_copy(handle)
+        self._lib.check(self._lib.lib().styler_peer_open(buf, ct.byref(p)), "peer_open")
+        self._mapped.append(p.value)
+        return p.value
+
+    def _tensor(self, ptr, nbytes):
+        raw = _RawDeviceMemory(ptr, nbytes)
+        self._keep.append(raw)
+        return torch.as_tensor(raw, device=self.device)
+
+    def _stream(self):
+        return self._ct.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def slice_ptr(self, rank, slot):
+        return self.recv_ptr + (rank * self.slots + slot) * self.stride
+
+    # -- protocol ----------------------------------------------------------------------------------------------------------
+    def buffer(self, slot, rank=None):
+        """uint8 view [nbytes] of (rank, slot) of the receive region (peer memory on every rank but dst)."""
+        return self._tensor(self.slice_ptr(self.rank if rank is None else rank, slot), self.nbytes)
+
+    @property
+    def remote(self):
+        return self.rank != self.dst
+
+    def begin(self, slot):
+        """Before the forward that writes slot `slot`: wait (stream order) until rank 0 has consumed its previous contents."""
+        self.uses[slot] += 1
+        if self.remote and self.uses[slot] > 1:
+            with torch.cuda.device(self.device):
+                self._lib.check(self._lib.lib().styler_peer_wait(self._ct.c_void_p(self.ack_ptr + 8 * slot), 1, 1,
+                                                               self.uses[slot] - 1, self._stream()), "peer_wait(ack)")
+
+    def commit(self, slot):
+        """After the forward: publish `ready` for this rank and slot (everything enqueued before it on the stream is visible)."""
+        if self.remote:
+            with torch.cuda.device(self.device):
+                self._lib.check(self._lib.lib().styler_peer_signal(self._ct.c_void_p(self.ready_ptr + 256 * self.rank + 8 * slot),
+                                                                 self.uses[slot], self._stream()), "peer_signal(ready)")
+
+    def collect(self, slot):
+        """Rank 0: stream-wait until every other rank has committed this use of `slot`; returns the per-rank byte buffers."""
+        assert not self.remote
+        with torch.cuda.device(self.device):
+            for r in range(self.world):
+                if r != self.dst:
+                    self._lib.check(self._lib.lib().styler_peer_wait(self._ct.c_void_p(self.ready_ptr + 256 * r + 8 * slot), 1, 1,
+                                                                   self.uses[slot], self._stream()), "peer_wait(ready)")
+        return [self.buffer(slot, r) for r in range(self.world)]
+
+    def release(self, slot):
+        """Rank 0: the consumer is done with `slot` (stream order): let the other ranks overwrite it."""
+        assert not self.remote
+        with torch.cuda.device(self.device):
+            for r in range(self.world):
+                if r != self.dst:
+                    self._lib.check(self._lib.lib().styler_peer_signal(self._ct.c_void_p(self.ack_remote[r] + 8 * slot),
+                                                                     self.uses[slot], self._stream()), "peer_signal(ack)")
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier()
+        for p in self._mapped:
+            self._lib.lib().styler_peer_close(self._ct.c_void_p(p))
+        self._mapped = []
+        if dist.is_initialized():
+            dist.barrier()
+        for p in self._own:
+            self._lib.lib().styler_peer_free(self._ct.c_void_p(p))
+        self._own = []
+
+
+class AsyncPeerGather:
+    """Drives PeerGather with the interface of AsyncGather (bench.py / serving loops): the ranks' forwards write their packed
+    results directly into rank 0's receive region; rank 0 collects and releases on a side stream so that its own next
+    forward is not held up by the slowest rank.
+
+        buf = g.begin(slot)            # every rank, before the forward (stream-waits for the slot to be free)
+        ... forward with engine.result_mirror = g.buffer(slot) (or a CUDA graph captured with it) ...
+        g.launch_packed(None, slot)    # every rank, after the forward: commit (+ rank 0: collect + release on the side stream)
+        g.wait()                       # join the side stream (end of a timed region / before reading `result`)
+    """
+
+    def __init__(self, device, nbytes, slots=2, dst=0):
+        self.pg = PeerGather(device, nbytes, slots, dst)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._done = {}
+        self.result = None
+
+    def buffer(self, slot):
+        return self.pg.buffer(slot)
+
+    @property
+    def remote(self):
+        return self.pg.remote
+
+    def begin(self, slot):
+        self.before_reuse(slot)
+        self.pg.begin(slot)
+
+    def launch_packed(self, packed, slot=0):
+        self.pg.commit(slot)
+        if not self.pg.remote:
+            main = torch.cuda.current_stream(self.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self.stream.wait_event(ready)
+            with torch.cuda.stream(self.stream):
+                self.result = self.pg.collect(slot)
+                self.pg.release(slot)
+                ev = self._done.get(slot)
+                if ev is None:
+                    ev = self._done[slot] = torch.cuda.Event()
+                ev.record(self.stream)
+
+    def before_reuse(self, slot=0):
+        ev = self._done.get(slot)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self.result
+
+    def close(self):
+        self.pg.close()

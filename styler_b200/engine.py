@@ -74,6 +74,7 @@ class Engine:
         self._pos_cache = {}
         self.inter = {}
         self.last_packed = None
+        self.result_mirror = None            # uint8 tensor of packed_nbytes(B, T) in PEER memory: forward() also writes its results there
         self.v_rowmajor = precision == "bf16"   # attention reads V row-major from the fused QKV buffer (MN-major B operand;
                                                # validated for kind::f16 only -- the fp32 modes keep the transposed-V layout)
         import os
@@ -152,6 +153,8 @@ class Engine:
                 wih = torch.cat([sd[L + "weight_ih_" + k], sd[L + "weight_ih_" + kr]], 0)
                 bias = torch.cat([sd[L + "bias_ih_" + k] + sd[L + "bias_hh_" + k],
                                   sd[L + "bias_ih_" + kr] + sd[L + "bias_hh_" + kr]], 0)
+                perm = ops.lstm_quad_order(wih.shape[0] // 8).to(wih.device)   # [dir][gate][unit] -> [dir][unit][gate]
+                wih, bias = wih[perm], bias[perm]
                 whh = torch.stack([sd[L + "weight_hh_" + k], sd[L + "weight_hh_" + kr]], 0)
                 br.lstm.append((self._w(wih), self._f32(bias), self._f32(whh)))
             w.branches.append(br)
@@ -299,9 +302,12 @@ class Engine:
         return t if self.dt == torch.float32 else ops.cast(t, self.dt)
 
     # ------------------------------------------------------------------------------------------ decode (styler.py:29-37)
-    def decode(self, x, mel_lens, mel_out=None, post_out=None):
+    def decode(self, x, mel_lens, mel_out=None, post_out=None, mel_mirror=None, post_mirror=None):
         """x [B,T,256] (activation dtype) -> (mel fp32 [B,T,80], mel_postnet fp32 [B,T,80]); the results are written into
-        mel_out / post_out when given (slices of the packed gather buffer)."""
+        mel_out / post_out when given (slices of the packed result buffer).  mel_mirror / post_mirror: second, WRITE-ONLY
+        destinations -- this rank's slice of rank 0's gather buffer mapped over NVLink (dist.PeerGather): mel_linear and the last
+        PostNet convolution store their fp32 results there from their own epilogues (`out2_f32`), so the gather is fused into
+        the tensor-core kernels that produce the mels."""
         B, T, _ = x.shape
         h = ops.add(x, pos=self._pos("dec", T))
         for W in self.w.dec_layers:
@@ -310,16 +316,20 @@ class Engine:
         if self.dt == torch.float32:
             ops.conv1d(h, self.w.mel[0], self.w.mel[1], out=mel, impl=self.impl)
             mel_t = mel
+            if mel_mirror is not None:
+                mel_mirror.copy_(mel)
         else:
-            mel_t = ops.conv1d(h, self.w.mel[0], self.w.mel[1], out_f32=mel, impl=self.impl)
+            mel_t = ops.conv1d(h, self.w.mel[0], self.w.mel[1], out_f32=mel, out2_f32=mel_mirror, impl=self.impl)
         if not self.w.postnet:                       # use_postnet=False (styler.py:33-36): mel_output_postnet = mel_output
+            if post_mirror is not None:
+                post_mirror.copy_(mel)
             return mel, mel
         p = mel_t
         for j in range(4):
             p = ops.conv1d(p, self.w.postnet[j][0], self.w.postnet[j][1], pad=2, act=ACT_TANH, impl=self.impl)
         post = post_out if post_out is not None else torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
-        ops.conv1d(p, self.w.postnet[4][0], self.w.postnet[4][1], pad=2, residual_f32=mel, out_f32=post, want_out=False,
-                   impl=self.impl)
+        ops.conv1d(p, self.w.postnet[4][0], self.w.postnet[4][1], pad=2, residual_f32=mel, out_f32=post, out2_f32=post_mirror,
+                   want_out=False, impl=self.impl)
         return mel, post
 
     # ------------------------------------------------------------------------------------------ style modeling
@@ -414,8 +424,15 @@ class Engine:
         # The four mel tensors and the lengths land in ONE contiguous buffer [mel | mel_noisy | postnet | postnet_noisy | len]
         # so that the data-parallel gather to rank 0 (dist.AsyncGather.launch_packed) is a single NCCL operation.
         packed, mel_out, post_out = (None, None, None) if not self.w.postnet else packed_views(B, T, dev)
-        mel2, post2 = self.decode(self._xx, out_len.repeat(2), mel_out, post_out)
+        mirror, mel_m, post_m = None, None, None
+        if self.result_mirror is not None:             # this rank's slice of rank 0's receive region (dist.PeerGather)
+            if packed is None or self.result_mirror.numel() != packed_nbytes(B, T):
+                raise ValueError("result_mirror must hold exactly %d bytes for B=%d, T=%d (and needs the PostNet)" % (packed_nbytes(B, T), B, T))
+            mirror, mel_m, post_m = packed_views(B, T, dev, self.result_mirror)
+        mel2, post2 = self.decode(self._xx, out_len.repeat(2), mel_out, post_out, mel_m, post_m)
         self.join_audio_streams()                      # the DAT posteriors (side streams) are outputs of this forward
+        if mirror is not None:
+            mirror[1].copy_(out_len)
         if packed is not None:
             packed[1].copy_(out_len)
         self.last_packed = packed[0] if packed is not None else None

@@ -400,7 +400,9 @@ class GraphedSTYLER:
     capture with the `max_mel_len` you are willing to pad to.
     """
 
-    def __init__(self, model, example_args, example_kwargs, warmup=2):
+    def __init__(self, model, example_args, example_kwargs, warmup=2, result_mirror=None):
+        """result_mirror: uint8 tensor of engine.packed_nbytes(B, T) that ALSO receives the four mels + lengths, written by the
+        epilogues of the producing kernels: this rank's slice of rank 0's peer-mapped gather region (dist.PeerGather)."""
         self.model = model
         eng = model._engine_for()
         self._eng = eng          # the graph holds raw pointers into this engine's packed weights / tables / side streams
@@ -413,16 +415,20 @@ class GraphedSTYLER:
         self.static_kwargs["max_mel_len"] = T
         eng._pos("dec", T)                                   # position tables beyond max_seq_len are built on the host: do it now
         eng._pos("enc", self.static_args[0].shape[1])
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                model(*self.static_args, **self.static_kwargs)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_out = model(*self.static_args, **self.static_kwargs)
+        eng.result_mirror = result_mirror
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    model(*self.static_args, **self.static_kwargs)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_out = model(*self.static_args, **self.static_kwargs)
+        finally:
+            eng.result_mirror = None
         self.packed = eng.last_packed      # the captured results as one byte buffer (dist.AsyncGather.launch_packed)
 
     def __call__(self, *args, **kwargs):

@@ -48,13 +48,14 @@ def _v3(t, name="tensor"):
 @_on_tensor_device
 def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=None, residual_f32=None, ln=None, ln_eps=1e-5,
            act2=ACT_NONE, lens=None, dot=None, out=None, want_out=True, out_f32=None, vt=None, vt_col0=0,
-           impl=IMPL_AUTO, dilation=1, act_slope=0.0, residual_inv_lrelu=False):
+           impl=IMPL_AUTO, dilation=1, act_slope=0.0, residual_inv_lrelu=False, out2_f32=None):
     """y = epilogue(conv1d(x, w)) -- see styler_conv1d_fwd.  x [B,T,Cin]; w packed [KS,N,Cin] (same dtype as x).
 
     residual: [B,T,N] tensor added after `act`; residual_row: [B,N] row broadcast over t instead.
     ln: (gamma, beta) fp32 -> LayerNorm over N;  dot: (w[N] fp32, bias float) -> also returns the [B,T] fp32 row dot.
     vt: preallocated [B, N - vt_col0, Tpad] tensor receiving columns >= vt_col0 transposed.
     dilation: tap spacing; act_slope: negative-side slope of ACT_LRELU; residual_inv_lrelu: `residual` holds lrelu(r).
+    out2_f32: second fp32 destination with the strides of out_f32 (e.g. a peer-mapped slice of rank 0's gather buffer).
     Returns out (dtype of x) unless want_out=False; with `dot`, returns (out_or_None, dot_out).
     """
     x, x_bs, x_ld = _v3(x, "x")
@@ -107,6 +108,10 @@ def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=
         f, f_bs, f_ld = _v3(out_f32, "out_f32")
         assert f.dtype == torch.float32
         a.out_f32, a.of_bstride, a.of_ld = f.data_ptr(), f_bs, f_ld
+    if out2_f32 is not None:
+        f2, f2_bs, f2_ld = _v3(out2_f32, "out2_f32")
+        assert out_f32 is not None and f2.dtype == torch.float32 and (f2_bs, f2_ld) == (f_bs, f_ld) and f2.shape == f.shape
+        a.out2_f32 = f2.data_ptr()
     if vt is not None:
         assert vt.dtype == x.dtype and vt.dim() == 3 and vt.stride(2) == 1
         a.vt, a.vt_col0, a.vt_bstride, a.vt_ld = vt.data_ptr(), vt_col0, int(vt.stride(0)), int(vt.stride(1))
@@ -260,9 +265,17 @@ def mel_calibrator(x, mel_len, src_len, Lmax, out=None):
     return out
 
 
+def lstm_quad_order(H):
+    """Row permutation that takes the stacked input projection [W_ih_fwd ; W_ih_rev] (PyTorch order [dir][gate i,f,g,o][unit])
+    to the order the BiLSTM kernel reads gx in: [dir][unit][gate] -- the four gates of a unit are adjacent, element t of a
+    direction's row belongs to thread t."""
+    idx = torch.arange(8 * H).view(2, 4, H)            # value = original row
+    return idx.permute(0, 2, 1).reshape(-1)
+
+
 @_on_tensor_device
 def bilstm_layer(gx, whh, dtype, out=None):
-    """gx fp32 [B,L,8H]; whh fp32 [2,4H,H] -> [B,L,2H]."""
+    """gx fp32 [B,L,8H] in quad order (see lstm_quad_order); whh fp32 [2,4H,H] (PyTorch row order) -> [B,L,2H]."""
     B, Ln, G8 = gx.shape
     H = G8 // 8
     assert gx.is_contiguous() and gx.dtype == torch.float32 and whh.is_contiguous()

@@ -135,6 +135,9 @@ PERSIST_CASES = [
     ("pred_k3_relu_ln",    10, 2100, 256,  256, 3, dict(act=1, ln=True)),
     ("mel_linear_n64_res", 40, 1000, 256,  64,  1, dict(res=True)),
     ("postnet_in_tanh",    10, 2100, 80,   512, 5, dict(act=2)),
+    # 320-channel audio-encoder conv: full-width N tile (one A stage, two MMAs of 160 columns), >= 148 M tiles
+    ("audio_k5_320_wide",  10, 2100, 320,  320, 5, dict()),
+    ("audio_k5_320_wide_relu_res", 9, 2300, 320, 320, 5, dict(act=1, res=True)),
 ]
 
 
@@ -411,6 +414,8 @@ def test_bilstm(cuda, H, Cin):
         b = torch.cat([sd[p + "bias_ih_l%d" % layer] + sd[p + "bias_hh_l%d" % layer],
                        sd[p + "bias_ih_l%d_reverse" % layer] + sd[p + "bias_hh_l%d_reverse" % layer]], 0)
         whh = torch.stack([sd[p + "weight_hh_l%d" % layer], sd[p + "weight_hh_l%d_reverse" % layer]], 0)
+        perm = ops.lstm_quad_order(H)                      # the kernel reads gx as [dir][unit][gate]
+        wih, b = wih[perm], b[perm]
         gx = torch.empty(B, Ln, 8 * H, device=cuda)
         ops.conv1d(cur, wih.unsqueeze(0).contiguous().to(cuda), b.to(cuda), out_f32=gx, want_out=False, impl=ops.IMPL_SIMT)
         cur = ops.bilstm_layer(gx, whh.contiguous().to(cuda), torch.float32)
