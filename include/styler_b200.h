@@ -72,6 +72,10 @@ typedef struct {
   float* out2_f32;                                       /* optional SECOND fp32 destination, same strides as out_f32 (requires
                                                             out_f32): e.g. the slice of rank 0's peer-mapped gather buffer, so
                                                             the result crosses NVLink from the producing epilogue */
+  float* gn_partial;                                     /* optional (tensor-core path, no LN / dot / vt, N % 16 == 0): GroupNorm
+                                                            partial statistics of the OUTPUT, fp32 [B][ceil(T/128)][N/16][2] =
+                                                            (sum, sum of squares) over 16 channels x the 128-row tile; finished by
+                                                            styler_groupnorm_relu_partial_fwd (no separate statistics pass) */
 } styler_conv1d_args;
 int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream);
 
@@ -98,6 +102,44 @@ int styler_fftblock_fwd(const styler_fft_weights* w, const void* x, int64_t x_bs
  * _read synchronises them, returns count / summed ms / (B, T) of the last one and resets. */
 int styler_debug_ffn1_timing(int32_t enable, int32_t min_T);
 int styler_debug_ffn1_timing_read(float* total_ms, int32_t* launches, int64_t* last_B, int64_t* last_T);
+
+/* ---- Composite entries: whole sub-graphs of the forward in one native call, intermediates in one caller-owned workspace.
+ * StylePredictor.forward (modules.py:457-465): Conv(k)+ReLU+LN, Conv(k)+ReLU+LN, Linear(C->1), masked_fill -> out fp32 [B][T]. */
+typedef struct {
+  int32_t c_in, channels, ks;                             /* 256, 256, 3 */
+  const void* w1; const float* b1; const float* ln1_gamma; const float* ln1_beta;   /* [ks][channels][c_in] */
+  const void* w2; const float* b2; const float* ln2_gamma; const float* ln2_beta;   /* [ks][channels][channels] */
+  const float* lin_w; float lin_b;                        /* Linear(channels -> 1) */
+  float ln_eps;
+} styler_predictor_weights;
+int64_t styler_predictor_workspace_bytes(int32_t B, int32_t T, int32_t channels, int32_t dtype);
+int styler_predictor_fwd(const styler_predictor_weights* w, const void* x, int64_t x_bstride, int32_t x_ld,
+                         const int64_t* lens, float* out, int32_t B, int32_t T, int32_t dtype, int32_t impl,
+                         void* workspace, int64_t ws_bytes, void* stream);
+/* PostNet.forward + the residual add of styler.py:34 (transformer/Layers.py:121-130; eval BatchNorm folded into w/b at pack
+ * time): mel_act = the mel in the activation dtype [B][T][n_mel] (conv input), mel_f32 = the fp32 mel (residual);
+ * post_out (and post_out2 if not NULL, e.g. a peer-mapped gather slice) = postnet(mel) + mel, fp32 [B][T][n_mel]. */
+typedef struct {
+  int32_t n_layers, n_mel, channels, ks;                  /* 5, 80, 512, 5 */
+  const void* w[8]; const float* b[8];                    /* layer j: [ks][channels or n_mel][n_mel or channels] */
+} styler_postnet_weights;
+int64_t styler_postnet_workspace_bytes(int32_t B, int32_t T, int32_t channels, int32_t dtype);
+int styler_postnet_fwd(const styler_postnet_weights* w, const void* mel_act, const float* mel_f32, float* post_out,
+                       float* post_out2, int32_t B, int32_t T, int32_t dtype, int32_t impl, void* workspace,
+                       int64_t ws_bytes, void* stream);
+/* STYLER.decode (styler.py:29-37) = Decoder.forward (transformer/Models.py:111-135: x + pos rows, n_layers FFT blocks) +
+ * mel_linear + PostNet + residual.  x: [B][T][d_model] contiguous, activation dtype; pos: fp32 [T][d_model] (the caller
+ * supplies rows beyond max_seq_len, Models.py:120-122); mel_out / post_out: fp32 [B][T][n_mel] contiguous; mel_out2 /
+ * post_out2: optional second destinations (same layout).  postnet == NULL: use_postnet=False, post_out is not written. */
+typedef struct {
+  int32_t n_layers; const styler_fft_weights* layers;     /* array of n_layers */
+  const void* mel_w; const float* mel_b; int32_t n_mel;   /* [1][n_mel][d_model] */
+  const styler_postnet_weights* postnet;                  /* or NULL */
+} styler_decoder_weights;
+int64_t styler_decoder_workspace_bytes(const styler_decoder_weights* w, int32_t B, int32_t T, int32_t dtype);
+int styler_decoder_fwd(const styler_decoder_weights* w, const void* x, const float* pos, const int64_t* lens, float* mel_out,
+                       float* post_out, float* mel_out2, float* post_out2, int32_t B, int32_t T, int32_t dtype, int32_t impl,
+                       void* workspace, int64_t ws_bytes, void* stream);
 
 /* ---- Scaled-dot-product multi-head self-attention (transformer/Modules.py:14-25, SubLayers.py:44-56) ----
  * qk: [B][T][2*H*64] (Q columns then K columns, head h at h*64; 1/temperature already folded into Q),
@@ -131,6 +173,12 @@ int styler_quantize_index_fwd(const float* x, int32_t* idx, int64_t n, void* str
 int styler_onehot_conv_fwd(const int32_t* idx, const float* wg, const float* bias, void* out, int32_t B, int32_t T,
                            int32_t C, int32_t nidx, int32_t KS, int32_t dtype, void* stream);
 
+/* Same normalisation from the partial statistics a convolution left in `partial` (styler_conv1d_args.gn_partial, 16 channels
+ * per group, n_part = ceil(T/128) tiles per utterance): a B x groups finalize (fp64 combine, fixed order) + the apply pass.
+ * stats_ws: fp32 [B][C/16][2]. */
+int styler_groupnorm_relu_partial_fwd(void* x, int64_t bstride, int32_t ld, const float* gamma, const float* beta,
+                                      const float* partial, int32_t n_part, float* stats_ws, int32_t B, int32_t T, int32_t C,
+                                      float eps, int32_t dtype, void* stream);
 /* ---- GroupNorm(C/16 groups) over (16 channels x ALL T incl. padding) + ReLU, in place (modules.py:113,168-172) */
 int styler_groupnorm_relu_fwd(void* x, int64_t bstride, int32_t ld, const float* gamma, const float* beta,
                               float* stats_ws /* [B*C/16*2] */, int32_t B, int32_t T, int32_t C, int32_t ch_per_group,

@@ -33,7 +33,7 @@ class Conv1dArgs(ctypes.Structure):
         ("vt", c_vp), ("vt_col0", c_i32), ("vt_bstride", c_i64), ("vt_ld", c_i32),
         ("dtype", c_i32), ("impl", c_i32),
         ("dilation", c_i32), ("act_slope", c_f32), ("residual_inv_lrelu", c_i32),
-        ("out2_f32", c_vp),
+        ("out2_f32", c_vp), ("gn_partial", c_vp),
     ]
 
 
@@ -47,6 +47,30 @@ class FftWeights(ctypes.Structure):
         ("w2", c_vp), ("b2", c_vp), ("ks2", c_i32),
         ("ln2_gamma", c_vp), ("ln2_beta", c_vp),
         ("ln_eps", c_f32),
+    ]
+
+
+class PredictorWeights(ctypes.Structure):
+    _fields_ = [
+        ("c_in", c_i32), ("channels", c_i32), ("ks", c_i32),
+        ("w1", c_vp), ("b1", c_vp), ("ln1_gamma", c_vp), ("ln1_beta", c_vp),
+        ("w2", c_vp), ("b2", c_vp), ("ln2_gamma", c_vp), ("ln2_beta", c_vp),
+        ("lin_w", c_vp), ("lin_b", c_f32), ("ln_eps", c_f32),
+    ]
+
+
+class PostnetWeights(ctypes.Structure):
+    _fields_ = [
+        ("n_layers", c_i32), ("n_mel", c_i32), ("channels", c_i32), ("ks", c_i32),
+        ("w", c_vp * 8), ("b", c_vp * 8),
+    ]
+
+
+class DecoderWeights(ctypes.Structure):
+    _fields_ = [
+        ("n_layers", c_i32), ("layers", ctypes.POINTER(FftWeights)),
+        ("mel_w", c_vp), ("mel_b", c_vp), ("n_mel", c_i32),
+        ("postnet", ctypes.POINTER(PostnetWeights)),
     ]
 
 
@@ -68,6 +92,7 @@ _SIGNATURES = {
     "styler_quantize_index_fwd": [c_vp, c_vp, c_i64, c_vp],
     "styler_onehot_conv_fwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "styler_groupnorm_relu_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp],
+    "styler_groupnorm_relu_partial_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp],
     "styler_mel_calibrator_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
                                   c_i32, c_vp],
     "styler_bilstm_layer_fwd": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
@@ -84,6 +109,14 @@ _SIGNATURES = {
     "styler_f0_norm_fwd": [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp],
     "styler_debug_set_phase_buffer": [c_vp, c_i32],
     "styler_set_tuning": [ctypes.c_char_p, c_i32],
+    "styler_predictor_workspace_bytes": [c_i32, c_i32, c_i32, c_i32],
+    "styler_predictor_fwd": [ctypes.POINTER(PredictorWeights), c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp,
+                             c_i64, c_vp],
+    "styler_postnet_workspace_bytes": [c_i32, c_i32, c_i32, c_i32],
+    "styler_postnet_fwd": [ctypes.POINTER(PostnetWeights), c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp],
+    "styler_decoder_workspace_bytes": [ctypes.POINTER(DecoderWeights), c_i32, c_i32, c_i32],
+    "styler_decoder_fwd": [ctypes.POINTER(DecoderWeights), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
+                           c_vp, c_i64, c_vp],
     "styler_peer_alloc": [c_i64, ctypes.POINTER(c_vp), c_vp],
     "styler_peer_open": [c_vp, ctypes.POINTER(c_vp)],
     "styler_peer_close": [c_vp],
@@ -114,6 +147,8 @@ def lib():
     h.styler_last_error.restype = ctypes.c_char_p
     h.styler_launch_count.restype = ctypes.c_int64
     h.styler_fftblock_workspace_bytes.restype = ctypes.c_int64
+    for name in ("styler_predictor_workspace_bytes", "styler_postnet_workspace_bytes", "styler_decoder_workspace_bytes"):
+        getattr(h, name).restype = ctypes.c_int64
     _lib = h
     return h
 

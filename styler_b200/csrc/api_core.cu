@@ -35,7 +35,7 @@ struct TuneDef { const char* name; int dflt, lo, hi; };
 // pipeline-depth overrides;  PDL: programmatic dependent launch (off: measured 8.71 ms/step with it vs 8.07 without);
 // ATTN_PERSIST: persistent attention CTAs (0 | 1);  TC_WIDE: full-width N tile (two MMAs per k-step) for 256 < N <= 512
 const TuneDef kTune[TUNE_COUNT] = {{"TC_2CTA", 1, 0, 2}, {"TC_PERSIST", 1, 0, 2}, {"CONV_WIN", 1, 0, 1}, {"TC_BN", 0, 0, 256},
-                                   {"TC_SMEM_KB", 110, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}, {"TC_WIDE", 1, 0, 1}};
+                                   {"TC_SMEM_KB", 113, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}, {"TC_WIDE", 1, 0, 1}};
 std::atomic<int> g_tune[TUNE_COUNT];          // 0 = not resolved yet, else value + 1
 }  // namespace
 

@@ -230,6 +230,7 @@ extern "C" int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream) {
   if (impl == STYLER_IMPL_AUTO) impl = conv1d_tc_supported(*a, nullptr) && a->B * a->T >= 64 ? STYLER_IMPL_TC : STYLER_IMPL_SIMT;
   if (impl == STYLER_IMPL_TC) return conv1d_tc(*a, s);
   SB_REQUIRE(impl == STYLER_IMPL_SIMT, "conv1d: bad impl %d", a->impl);
+  SB_REQUIRE(a->gn_partial == nullptr, "conv1d: gn_partial (fused GroupNorm statistics) exists on the tensor-core path only");
   return conv1d_simt(*a, s);
 }
 

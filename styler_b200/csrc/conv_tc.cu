@@ -52,6 +52,11 @@ struct EpiParams {
   void* out; long long o_bstride; int o_ld;
   float* out_f32; long long of_bstride; int of_ld;
   float* out2_f32;            // optional second fp32 destination (same strides): peer-mapped gather slice
+  int contig_f32;             // non-staged epilogue, one N tile, full fp32 rows (of_ld == N): the tile's fp32 output (and fp32
+                              // residual) is one CONTIGUOUS block in global memory -> staged through plain smem, moved with
+                              // coalesced float4 accesses by all epilogue threads (mel_linear, last PostNet conv: N = 80)
+  float* gn_partial;          // optional GroupNorm partial sums [B][tiles_per_utt][N/16][2] (sum, sum of squares per 16 channels)
+  int n_total;                // N of the whole problem (gn_partial indexing)
   void* vt; int vt_col0; long long vt_bstride; int vt_ld;
 };
 
@@ -289,6 +294,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     const bool tile_to_vt = !FAST && ep.vt != nullptr && n0 >= ep.vt_col0;
     const bool st_out = FAST || (ep.stage_out != 0 && !tile_to_vt);            // TMA-store this tile's output from smem
     const bool st_res = FAST ? ep.residual != nullptr : ep.stage_res != 0;      // this tile's residual arrives in smem by TMA
+    // contiguous fp32 tile I/O (see EpiParams::contig_f32): s_of = [128][cld] output staging, s_rf = [128][cld] residual
+    const bool contig = !FAST && ep.contig_f32 != 0;
+    const int cld = BN + 4;                                            // padded row (floats): 16-byte aligned, fewer bank conflicts
+    float* s_of = reinterpret_cast<float*>(smem);
+    float* s_rf = s_of + kBM * cld;
+    const int rows_ok = min(kBM, Tlen - t0);                           // rows of this tile that exist
     const int t = t0 + r;
     const bool row_ok = t < Tlen;
     const uint32_t taddr = tmem_base + ab * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
@@ -362,6 +373,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
             rr[4 * g4] = f.x; rr[4 * g4 + 1] = f.y; rr[4 * g4 + 2] = f.z; rr[4 * g4 + 3] = f.w;
           }
         }
+      } else if (contig) {
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const float4 f = *reinterpret_cast<const float4*>(s_rf + r * cld + c + 4 * g4);
+          rr[4 * g4] = f.x; rr[4 * g4 + 1] = f.y; rr[4 * g4 + 2] = f.z; rr[4 * g4 + 3] = f.w;
+        }
       } else if (res_row_f != nullptr) {
         load16(res_row_f + c, rr);
       } else {
@@ -423,6 +440,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     if (st_res) mbar_wait(res_full, PERSIST ? (it & 1) : 0);
     else if (PERSIST && it > 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // thread 64 has seen the previous store drain
     if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
+    if (contig && has_res) {
+      const float* src = static_cast<const float*>(ep.residual) + b * ep.r_bstride + static_cast<long long>(t0) * BN;
+      const int n4 = rows_ok * (BN / 4);
+      for (int i = threadIdx.x - 64; i < n4; i += 256) {
+        const int rr_ = i / (BN / 4), c4 = i - rr_ * (BN / 4);
+        *reinterpret_cast<float4*>(s_rf + rr_ * cld + 4 * c4) = __ldg(reinterpret_cast<const float4*>(src) + i);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
 
     float mean = 0.f, rstd = 1.f, nmr = 0.f;   // nmr = -mean * rstd: (v - mean) * rstd = fma(v, rstd, nmr)
     if (has_ln) {
@@ -498,6 +524,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) DT<T>::st(vt_base + static_cast<long long>(c + i) * ep.vt_ld, v[i]);
         }
+      } else if (contig) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(s_of + r * cld + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       } else {
         store_out(c, v);
         if (row_ok) {
@@ -514,6 +544,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
         }
       }
     };
+    // GroupNorm statistics of the tile (modules.py:113 normalises 16-channel groups over ALL time steps of the padded grid):
+    // a 16-column chunk is exactly one group, a warp holds 32 of the tile's rows -> shuffle-reduce (sum, sum of squares) per
+    // chunk, the four lane-quarter warps meet in smem, one pair per (tile, group) goes to HBM.  The stand-alone statistics
+    // pass over the stored tensor (12 launches, ~15 us each per forward) disappears; fixed reduction order = deterministic.
+    float* s_gn = s_x;                                        // [4 quarters][BN/16][2]; s_x is otherwise used by LN / dot only
+    auto gn_accum = [&](int c, const float (&v)[16]) {
+      float sg = 0.f, qg = 0.f;
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { sg += v[i]; qg = fmaf(v[i], v[i], qg); }
+      }
+      sg = warp_sum(sg);
+      qg = warp_sum(qg);
+      if (lane == 0) { s_gn[(q * (BN / 16) + (c >> 4)) * 2] = sg; s_gn[(q * (BN / 16) + (c >> 4)) * 2 + 1] = qg; }
+    };
+    const bool do_gn = !LN && ep.gn_partial != nullptr;
     long long t_wait = 0;
     for (int c = c_begin; c < c_end; c += 32) {
       const bool two = c + 16 < c_end;
@@ -539,6 +585,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
         if (need_res) add16(v, xa);
       }
       act2f(v);
+      if (do_gn) gn_accum(c, v);
       finish_chunk(c, v);
       if (two) {
         if (has_ln) {
@@ -552,8 +599,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
           if (need_res) add16(v, xb);
         }
         act2f(v);
+        if (do_gn) gn_accum(c + 16, v);
         finish_chunk(c + 16, v);
       }
+    }
+    if (do_gn) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int te = threadIdx.x - 64;
+      if (te < BN / 16) {
+        float sg = 0.f, qg = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) { sg += s_gn[(qq * (BN / 16) + te) * 2]; qg += s_gn[(qq * (BN / 16) + te) * 2 + 1]; }
+        float* dst = ep.gn_partial + ((static_cast<long long>(b) * tiles_per_utt + t0 / kBM) * (ep.n_total / 16) + n0 / 16 + te) * 2;
+        dst[0] = sg; dst[1] = qg;
+      }
+      if (PERSIST) asm volatile("bar.sync 1, 256;" ::: "memory");   // s_gn is reused by this CTA's next tile
     }
     if (!FAST && ep.dot_out != nullptr) {               // row dot: sum the two column halves
       if (has_ln) asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone has consumed the LN exchange slots
@@ -565,6 +625,30 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
     if (dbg != nullptr && threadIdx.x == 64 && !has_ln) dbg[5] = dbg[4] + t_wait;   // non-LN tiles: slot 5 = TMEM ld+wait time
     long long t_pre_store = 0;
     if (dbg != nullptr) t_pre_store = clock64();
+    if (contig) {   // the tile's rows are one contiguous block of the fp32 output (and of the dtype output): coalesced copies
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const long long base = b * ep.of_bstride + static_cast<long long>(t0) * BN;
+      float4* dst = reinterpret_cast<float4*>(ep.out_f32 + base);
+      float4* dst2 = ep.out2_f32 != nullptr ? reinterpret_cast<float4*>(ep.out2_f32 + base) : nullptr;
+      T* dsto = ep.out != nullptr ? static_cast<T*>(ep.out) + b * ep.o_bstride + static_cast<long long>(t0) * BN : nullptr;
+      const int n4 = rows_ok * (BN / 4);
+      for (int i = threadIdx.x - 64; i < n4; i += 256) {
+        const int rr_ = i / (BN / 4), c4 = i - rr_ * (BN / 4);
+        const float4 f = *reinterpret_cast<const float4*>(s_of + rr_ * cld + 4 * c4);
+        dst[i] = f;
+        if (dst2 != nullptr) dst2[i] = f;                      // e.g. rank 0's receive buffer over NVLink
+        if (dsto != nullptr) {
+          if constexpr (sizeof(T) == 2) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(dsto)[i] = u;
+          } else {
+            reinterpret_cast<float4*>(dsto)[i] = f;
+          }
+        }
+      }
+    }
     if (st_out) {   // smem tile -> global with TMA (rows >= T are clipped by the tensor map)
       fence_proxy_async_smem();
       if (PERSIST) tc_fence_before();              // this tile's TMEM reads are ordered before the hand-back below
@@ -595,7 +679,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
   if (dbg != nullptr && threadIdx.x == 0) dbg[7] = clock64();
 }
 
-int smem_budget_bytes() { return tuning(TUNE_TC_SMEM_KB) * 1024; }
+// Operand-ring budget of a non-persistent CTA.  TWO CTAs must fit an SM: 228 KB per SM minus 1 KB the driver reserves per
+// CTA = 113 KB (115,712 B) each, INCLUDING the ~9.25 KB of barriers / parameter vectors / exchange behind the ring.  (Round 1
+// sized the ring alone at 110 KB: a 4 x 26 KB ring for N = 80 came to 115,968 B -- 256 B over -- and the last PostNet conv and
+// mel_linear silently ran one CTA per SM: 0.215 ms at B=128.)
+constexpr int kFixedSmemBytes = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*params*/ + 4096 /*exchange*/;
+int smem_budget_bytes() {
+  const int total = tuning(TUNE_TC_SMEM_KB) * 1024;
+  return (total < 115712 ? total : 115712) - kFixedSmemBytes;
+}
 // persistent form: 0 = one tile per CTA everywhere, 1 (default) = where two CTAs per SM still fit (two accumulators of <= 128
 // TMEM columns), 2 = also the one-CTA-per-SM form (N = 256 LayerNorm rows; measured slower: out-proj 0.037 -> 0.045 ms, its
 // epilogue is issue-bound and loses the second CTA's warps)
@@ -671,7 +763,7 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   const int stage_bytes = kAStageBytes + (cg2 ? BN / 2 : BN) * 128;
   const int staging_bytes = persist ? BN * es * kBM : 0;
   const bool wide = BN > 256;
-  const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + (wide ? 8192 : 4096) /*params*/ + 4096 /*exchange*/;
+  const int fixed_bytes = kFixedSmemBytes + (wide ? 4096 : 0) /*wide tile: 512-column parameter vectors*/;
   int stages = ((persist ? (ctas_per_sm == 2 ? 113 : 226) * 1024 - staging_bytes - fixed_bytes
                          : (wide ? 200 * 1024 : smem_budget_bytes()))) / stage_bytes;
   if (stages > (persist ? 4 : 8)) stages = persist ? 4 : 8;
@@ -730,6 +822,14 @@ int launch(const styler_conv1d_args& a, cudaStream_t stream) {
   ep.dot_w = a.dot_w; ep.dot_b = a.dot_b; ep.dot_out = a.dot_out;
   ep.out = a.out; ep.o_bstride = a.o_bstride; ep.o_ld = a.o_ld;
   ep.out_f32 = a.out_f32; ep.of_bstride = a.of_bstride; ep.of_ld = a.of_ld; ep.out2_f32 = a.out2_f32;
+  ep.gn_partial = a.gn_partial; ep.n_total = a.N;
+  // contiguous-tile staging for narrow fp32 outputs (see EpiParams): non-staged epilogue, one N tile, full rows everywhere
+  ep.contig_f32 = (!stage_out && a.out_f32 != nullptr && n_tiles == 1 && a.of_ld == a.N && a.N % 4 == 0 && a.vt == nullptr &&
+                   a.dot_w == nullptr && !has_ln && (a.out == nullptr || a.o_ld == a.N) &&
+                   (a.residual == nullptr || (a.residual_is_f32 && a.r_ld == a.N)) &&
+                   static_cast<size_t>(2) * kBM * (a.N + 4) * sizeof(float) <= static_cast<size_t>(stages) * stage_bytes &&
+                   (a.out == nullptr || (reinterpret_cast<uintptr_t>(a.out) % 8 == 0 && (a.o_bstride * es) % 8 == 0)))
+                      ? 1 : 0;
   ep.vt = a.vt; ep.vt_col0 = a.vt_col0; ep.vt_bstride = a.vt_bstride; ep.vt_ld = a.vt_ld;
 
   using KernFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, EpiParams, int, int, int, int, int, int, int, int, int, int);
@@ -792,6 +892,8 @@ bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why) {
   if (a.out_f32 != nullptr && (!aligned16(a.out_f32) || (a.of_ld % 4) != 0 || (a.of_bstride % 4) != 0))
     return fail("out_f32 not 16-byte aligned/strided");
   if (a.out2_f32 != nullptr && (a.out_f32 == nullptr || !aligned16(a.out2_f32))) return fail("out2_f32 needs out_f32 and 16-byte alignment");
+  if (a.gn_partial != nullptr && (a.ln_gamma != nullptr || a.dot_w != nullptr || a.vt != nullptr || a.N % 16 != 0))
+    return fail("gn_partial: plain conv epilogues with N % 16 == 0 only");
   const int res_es = a.residual_is_f32 ? 4 : es;
   if (a.residual != nullptr && (!aligned16(a.residual) || (static_cast<int64_t>(a.r_ld) * res_es) % 16 != 0 || (a.r_bstride * res_es) % 16 != 0))
     return fail("residual not 16-byte aligned/strided");
@@ -808,7 +910,7 @@ void set_phase_buffer(long long* buf, int cap) { g_phase_buf = buf; g_phase_cap 
 int conv1d_tc(const styler_conv1d_args& a, cudaStream_t s) {
   const char* why = nullptr;
   SB_REQUIRE(conv1d_tc_supported(a, &why), "conv1d_tc: unsupported arguments: %s", why ? why : "?");
-  if (conv1d_win_supported(a)) return conv1d_win(a, s);
+  if (a.gn_partial == nullptr && conv1d_win_supported(a)) return conv1d_win(a, s);
   if (a.dtype == STYLER_BF16) return launch<__nv_bfloat16>(a, s);
   return launch<float>(a, s);
 }

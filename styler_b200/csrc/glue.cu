@@ -226,6 +226,25 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
     stats[2 * blockIdx.x + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
 }
+// finalize from per-tile partial sums written by the conv epilogue: one thread per (b, group), fp64 combine in tile order
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int B, int groups, int n_part,
+                                   int Tn, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * groups) return;
+  const int b = i / groups, g = i % groups;
+  double a = 0, q = 0;
+  for (int p = 0; p < n_part; ++p) {
+    const float* src = partial + ((static_cast<long long>(b) * n_part + p) * groups + g) * 2;
+    a += static_cast<double>(src[0]);
+    q += static_cast<double>(src[1]);
+  }
+  const double n = static_cast<double>(Tn) * 16.0;
+  const double mean = a / n;
+  double var = q / n - mean * mean;
+  var = var < 0 ? 0 : var;
+  stats[2 * i] = static_cast<float>(mean);
+  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
 template <typename T>
 __global__ void gn_apply_relu_kernel(T* __restrict__ x, long long bs, int ld, const float* __restrict__ stats,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, int B, int Tn,
@@ -548,6 +567,23 @@ extern "C" int styler_groupnorm_relu_fwd(void* x, int64_t bstride, int32_t ld, c
   const long long n = static_cast<long long>(B) * T * (C / 8);
   SB_DISPATCH_DTYPE(dtype, TT, (gn_apply_relu_kernel<TT><<<blocks_for(n, 256), 256, 0, s>>>(
                                    static_cast<TT*>(x), bstride, ld, stats_ws, gamma, beta, B, T, C, ch_per_group)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int styler_groupnorm_relu_partial_fwd(void* x, int64_t bstride, int32_t ld, const float* gamma, const float* beta,
+                                                 const float* partial, int32_t n_part, float* stats_ws, int32_t B, int32_t T,
+                                                 int32_t C, float eps, int32_t dtype, void* stream) {
+  SB_REQUIRE(x && gamma && beta && partial && stats_ws, "groupnorm_partial: null pointer");
+  SB_REQUIRE(B > 0 && T > 0 && C % 16 == 0 && ld % 8 == 0 && bstride % 8 == 0 && al16(x) && n_part == (T + 127) / 128,
+             "groupnorm_partial: bad shape/alignment (n_part must be ceil(T/128))");
+  const int groups = C / 16;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  gn_finalize_kernel<<<blocks_for(static_cast<long long>(B) * groups, 128), 128, 0, s>>>(partial, stats_ws, B, groups, n_part, T, eps);
+  SB_LAUNCH_OK();
+  const long long n = static_cast<long long>(B) * T * (C / 8);
+  SB_DISPATCH_DTYPE(dtype, TT, (gn_apply_relu_kernel<TT><<<blocks_for(n, 256), 256, 0, s>>>(
+                                   static_cast<TT*>(x), bstride, ld, stats_ws, gamma, beta, B, T, C, 16)));
   SB_LAUNCH_OK();
   return 0;
 }

@@ -122,6 +122,7 @@ class Engine:
         W.ln2 = (self._f32(sd[q + "layer_norm_2.weight"]), self._f32(sd[q + "layer_norm_2.bias"]))
         W.lw = self._f32(sd[p + "linear_layer.weight"].reshape(-1))
         W.lb = float(sd[p + "linear_layer.bias"].reshape(-1)[0].item())
+        W.c_struct = ops.make_predictor_weights(W.c1, W.b1, W.ln1, W.c2, W.b2, W.ln2, W.lw, W.lb)   # styler_predictor_weights
         return W
 
     def _pack(self, sd):
@@ -191,6 +192,7 @@ class Engine:
             rm, rv = sd[q + "1.running_mean"].to(self.device, torch.float32), sd[q + "1.running_var"].to(self.device, torch.float32)
             scale = g / torch.sqrt(rv + 1e-5)
             w.postnet.append((self._w(cw * scale[:, None, None]), self._f32((cb - rm) * scale + be)))
+        w.dec_struct = ops.make_decoder_weights([W.c_struct for W in w.dec_layers], w.mel[0], w.mel[1], w.postnet)
         self.w = w
 
     # ------------------------------------------------------------------------------------------ building blocks
@@ -216,20 +218,26 @@ class Engine:
         return self.fft_block(x, src_len, self.w.enc_layers[1], out=out)
 
     def predictor(self, x, lens, W):
-        """modules.py:457-465: Conv k3 + ReLU + LN, Conv k3 + ReLU + LN, Linear(256->1), masked_fill."""
-        h = ops.conv1d(x, W.c1, W.b1, pad=1, act=ACT_RELU, ln=W.ln1, impl=self.impl)
-        _, d = ops.conv1d(h, W.c2, W.b2, pad=1, act=ACT_RELU, ln=W.ln2, lens=lens, dot=(W.lw, W.lb),
-                          want_out=self.precision == "fp32", impl=self.impl)
-        return d
+        """modules.py:457-465: Conv k3 + ReLU + LN, Conv k3 + ReLU + LN, Linear(256->1), masked_fill -- one native call."""
+        return ops.predictor(x, W.c_struct, lens, impl=self.impl)
 
     def _audio_branch(self, br, xin, mel_len, src_len, L):
         x = None
         for j, (cw, cb, g, be) in enumerate(br.convs):
             if j == 0 and br.onehot:
                 x = ops.onehot_conv(xin, cw, cb, self.dt)
+                ops.groupnorm_relu_(x, g, be, 16, 1e-5)
+                continue
+            src = xin if j == 0 else x
+            B, Tr, N = src.shape[0], src.shape[1], cw.shape[1]
+            if self.impl != IMPL_SIMT and B * Tr >= 64:
+                # tensor-core conv: the GroupNorm statistics come out of its epilogue (no separate pass over the tensor)
+                part = torch.empty(B, (Tr + 127) // 128, N // 16, 2, device=src.device, dtype=torch.float32)
+                x = ops.conv1d(src, cw, cb, pad=2, impl=IMPL_TC, gn_partial=part)
+                ops.groupnorm_relu_partial_(x, g, be, part, 1e-5)
             else:
-                x = ops.conv1d(xin if j == 0 else x, cw, cb, pad=2, impl=self.impl)
-            ops.groupnorm_relu_(x, g, be, 16, 1e-5)
+                x = ops.conv1d(src, cw, cb, pad=2, impl=self.impl)
+                ops.groupnorm_relu_(x, g, be, 16, 1e-5)
         c = ops.mel_calibrator(x, mel_len, src_len, L)
         for (wih, bias, whh) in br.lstm:
             B = c.shape[0]
@@ -308,28 +316,13 @@ class Engine:
         destinations -- this rank's slice of rank 0's gather buffer mapped over NVLink (dist.PeerGather): mel_linear and the last
         PostNet convolution store their fp32 results there from their own epilogues (`out2_f32`), so the gather is fused into
         the tensor-core kernels that produce the mels."""
-        B, T, _ = x.shape
-        h = ops.add(x, pos=self._pos("dec", T))
-        for W in self.w.dec_layers:
-            h = self.fft_block(h, mel_lens, W)
-        mel = mel_out if mel_out is not None else torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
-        if self.dt == torch.float32:
-            ops.conv1d(h, self.w.mel[0], self.w.mel[1], out=mel, impl=self.impl)
-            mel_t = mel
-            if mel_mirror is not None:
-                mel_mirror.copy_(mel)
-        else:
-            mel_t = ops.conv1d(h, self.w.mel[0], self.w.mel[1], out_f32=mel, out2_f32=mel_mirror, impl=self.impl)
-        if not self.w.postnet:                       # use_postnet=False (styler.py:33-36): mel_output_postnet = mel_output
+        T = x.shape[1]
+        mel, post = ops.decoder(x.contiguous(), self.w.dec_struct, self._pos("dec", T), mel_lens, mel_out=mel_out, post_out=post_out,
+                                mel_out2=mel_mirror, post_out2=post_mirror, impl=self.impl)
+        if post is None:                             # use_postnet=False (styler.py:33-36): mel_output_postnet = mel_output
             if post_mirror is not None:
                 post_mirror.copy_(mel)
             return mel, mel
-        p = mel_t
-        for j in range(4):
-            p = ops.conv1d(p, self.w.postnet[j][0], self.w.postnet[j][1], pad=2, act=ACT_TANH, impl=self.impl)
-        post = post_out if post_out is not None else torch.empty(B, T, 80, device=x.device, dtype=torch.float32)
-        ops.conv1d(p, self.w.postnet[4][0], self.w.postnet[4][1], pad=2, residual_f32=mel, out_f32=post, out2_f32=post_mirror,
-                   want_out=False, impl=self.impl)
         return mel, post
 
     # ------------------------------------------------------------------------------------------ style modeling

@@ -431,7 +431,7 @@ class GraphedSTYLER:
             eng.result_mirror = None
         self.packed = eng.last_packed      # the captured results as one byte buffer (dist.AsyncGather.launch_packed)
 
-    def __call__(self, *args, **kwargs):
+    def _check(self, kwargs):
         if self.model._engine is not self._eng:
             raise RuntimeError("GraphedSTYLER: the model was moved / reloaded / re-precisioned after capture (its packed "
                                "weights were released); build a new GraphedSTYLER")
@@ -440,6 +440,10 @@ class GraphedSTYLER:
                     not (k == "max_mel_len" and v is None):
                 raise ValueError("GraphedSTYLER: %s=%r differs from the captured %r (scalars are baked into the graph)"
                                  % (k, v, self.static_kwargs[k]))
+
+    def load_inputs(self, *args, **kwargs):
+        """Copy new inputs (device or pinned-host tensors) into the captured static buffers on the current stream."""
+        self._check(kwargs)
         for dst, src in zip(self.static_args, args):
             if torch.is_tensor(dst):
                 dst.copy_(src, non_blocking=True)
@@ -447,5 +451,14 @@ class GraphedSTYLER:
             dst = self.static_kwargs.get(k)
             if torch.is_tensor(dst):
                 dst.copy_(v, non_blocking=True)
+
+    def replay(self):
+        """Replay the captured forward on the current stream over whatever the static buffers hold; returns the static outputs
+        (overwritten by the next replay)."""
+        self._check({})
         self.graph.replay()
         return self.static_out
+
+    def __call__(self, *args, **kwargs):
+        self.load_inputs(*args, **kwargs)
+        return self.replay()

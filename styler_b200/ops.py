@@ -48,7 +48,7 @@ def _v3(t, name="tensor"):
 @_on_tensor_device
 def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=None, residual_f32=None, ln=None, ln_eps=1e-5,
            act2=ACT_NONE, lens=None, dot=None, out=None, want_out=True, out_f32=None, vt=None, vt_col0=0,
-           impl=IMPL_AUTO, dilation=1, act_slope=0.0, residual_inv_lrelu=False, out2_f32=None):
+           impl=IMPL_AUTO, dilation=1, act_slope=0.0, residual_inv_lrelu=False, out2_f32=None, gn_partial=None):
     """y = epilogue(conv1d(x, w)) -- see styler_conv1d_fwd.  x [B,T,Cin]; w packed [KS,N,Cin] (same dtype as x).
 
     residual: [B,T,N] tensor added after `act`; residual_row: [B,N] row broadcast over t instead.
@@ -56,6 +56,7 @@ def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=
     vt: preallocated [B, N - vt_col0, Tpad] tensor receiving columns >= vt_col0 transposed.
     dilation: tap spacing; act_slope: negative-side slope of ACT_LRELU; residual_inv_lrelu: `residual` holds lrelu(r).
     out2_f32: second fp32 destination with the strides of out_f32 (e.g. a peer-mapped slice of rank 0's gather buffer).
+    gn_partial: fp32 [B, ceil(T/128), N/16, 2] receiving the GroupNorm partial sums of the output (tensor-core path only).
     Returns out (dtype of x) unless want_out=False; with `dot`, returns (out_or_None, dot_out).
     """
     x, x_bs, x_ld = _v3(x, "x")
@@ -115,6 +116,9 @@ def conv1d(x, w, bias=None, *, pad=0, act=ACT_NONE, residual=None, residual_row=
     if vt is not None:
         assert vt.dtype == x.dtype and vt.dim() == 3 and vt.stride(2) == 1
         a.vt, a.vt_col0, a.vt_bstride, a.vt_ld = vt.data_ptr(), vt_col0, int(vt.stride(0)), int(vt.stride(1))
+    if gn_partial is not None:
+        assert gn_partial.dtype == torch.float32 and gn_partial.is_contiguous() and gn_partial.shape == (B, (T + 127) // 128, N // 16, 2)
+        a.gn_partial = gn_partial.data_ptr()
     a.dtype, a.impl = L.dtype_code(x.dtype), impl
     L.check(L.lib().styler_conv1d_fwd(ctypes.byref(a), L.stream_ptr()), "conv1d")
     if dot is not None:
@@ -151,6 +155,70 @@ def fftblock(x, fw, lens, *, out=None, impl=IMPL_AUTO):
     L.check(L.lib().styler_fftblock_fwd(ctypes.byref(fw), L.ptr(x), x_bs, x_ld, L.ptr(o), o_bs, o_ld, L.ptr(lens), B, T, code,
                                         impl, L.ptr(ws), nbytes, L.stream_ptr()), "fftblock")
     return out
+
+
+def make_predictor_weights(c1, b1, ln1, c2, b2, ln2, lw, lb, ln_eps=1e-5):
+    """styler_predictor_weights over already packed, device-resident tensors (kept alive by the returned object)."""
+    pw = L.PredictorWeights()
+    pw.ks, pw.channels, pw.c_in = c1.shape[0], c1.shape[1], c1.shape[2]
+    pw.w1, pw.b1, pw.ln1_gamma, pw.ln1_beta = c1.data_ptr(), b1.data_ptr(), ln1[0].data_ptr(), ln1[1].data_ptr()
+    pw.w2, pw.b2, pw.ln2_gamma, pw.ln2_beta = c2.data_ptr(), b2.data_ptr(), ln2[0].data_ptr(), ln2[1].data_ptr()
+    pw.lin_w, pw.lin_b, pw.ln_eps = lw.data_ptr(), float(lb), ln_eps
+    pw._keep = (c1, b1, ln1, c2, b2, ln2, lw)
+    return pw
+
+
+def make_decoder_weights(fft_structs, mel_w, mel_b, postnet):
+    """styler_decoder_weights: `fft_structs` = list of FftWeights, `postnet` = list of (w [KS,N,Cin], b) or empty."""
+    dw = L.DecoderWeights()
+    arr = (L.FftWeights * len(fft_structs))(*fft_structs)
+    dw.n_layers, dw.layers = len(fft_structs), arr
+    dw.mel_w, dw.mel_b, dw.n_mel = mel_w.data_ptr(), mel_b.data_ptr(), mel_w.shape[1]
+    pn = None
+    if postnet:
+        pn = L.PostnetWeights()
+        pn.n_layers, pn.n_mel, pn.channels, pn.ks = len(postnet), mel_w.shape[1], postnet[0][0].shape[1], postnet[0][0].shape[0]
+        for j, (w, b) in enumerate(postnet):
+            pn.w[j], pn.b[j] = w.data_ptr(), b.data_ptr()
+        dw.postnet = ctypes.pointer(pn)
+    dw._keep = (arr, fft_structs, mel_w, mel_b, postnet, pn)
+    return dw
+
+
+@_on_tensor_device
+def predictor(x, pw, lens, *, impl=IMPL_AUTO):
+    """StylePredictor.forward in one native call (styler_predictor_fwd): x [B,T,C] view -> fp32 [B,T]."""
+    x, x_bs, x_ld = _v3(x, "x")
+    B, T, _ = x.shape
+    code = L.dtype_code(x.dtype)
+    out = torch.empty(B, T, device=x.device, dtype=torch.float32)
+    nbytes = int(L.lib().styler_predictor_workspace_bytes(B, T, pw.channels, code))
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    L.check(L.lib().styler_predictor_fwd(ctypes.byref(pw), L.ptr(x), x_bs, x_ld, L.ptr(lens), L.ptr(out), B, T, code, impl,
+                                         L.ptr(ws), nbytes, L.stream_ptr()), "predictor")
+    return out
+
+
+@_on_tensor_device
+def decoder(x, dw, pos, lens, *, mel_out=None, post_out=None, mel_out2=None, post_out2=None, impl=IMPL_AUTO):
+    """STYLER.decode in one native call (styler_decoder_fwd): x [B,T,D] contiguous -> (mel fp32 [B,T,n_mel], post fp32 or None)."""
+    assert x.is_contiguous() and pos.is_contiguous() and pos.dtype == torch.float32 and pos.shape[0] >= x.shape[1]
+    B, T, _ = x.shape
+    code = L.dtype_code(x.dtype)
+    nm = dw.n_mel
+    has_post = bool(dw.postnet)
+    if mel_out is None:
+        mel_out = torch.empty(B, T, nm, device=x.device, dtype=torch.float32)
+    if post_out is None and has_post:
+        post_out = torch.empty(B, T, nm, device=x.device, dtype=torch.float32)
+    for t in (mel_out, post_out, mel_out2, post_out2):
+        assert t is None or (t.is_contiguous() and t.dtype == torch.float32 and t.shape == (B, T, nm))
+    nbytes = int(L.lib().styler_decoder_workspace_bytes(ctypes.byref(dw), B, T, code))
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    L.check(L.lib().styler_decoder_fwd(ctypes.byref(dw), L.ptr(x), L.ptr(pos), L.ptr(lens), L.ptr(mel_out), L.ptr(post_out),
+                                       L.ptr(mel_out2), L.ptr(post_out2) if has_post else None, B, T, code, impl, L.ptr(ws), nbytes,
+                                       L.stream_ptr()), "decoder")
+    return mel_out, (post_out if has_post else None)
 
 
 @_on_tensor_device
@@ -250,6 +318,18 @@ def groupnorm_relu_(x, gamma, beta, ch_per_group=16, eps=1e-5):
     ws = torch.empty(B * (C // ch_per_group) * 2, device=x.device, dtype=torch.float32)
     L.check(L.lib().styler_groupnorm_relu_fwd(L.ptr(x3), bs, ld, L.ptr(gamma), L.ptr(beta), L.ptr(ws), B, T, C,
                                               ch_per_group, eps, L.dtype_code(x.dtype), L.stream_ptr()), "groupnorm_relu")
+    return x
+
+
+@_on_tensor_device
+def groupnorm_relu_partial_(x, gamma, beta, partial, eps=1e-5):
+    """GroupNorm(16 channels per group) + ReLU in place from the partial statistics the producing conv1d left in `partial`."""
+    x3, bs, ld = _v3(x, "x")
+    B, T, C = x3.shape
+    ws = torch.empty(B * (C // 16) * 2, device=x.device, dtype=torch.float32)
+    L.check(L.lib().styler_groupnorm_relu_partial_fwd(L.ptr(x3), bs, ld, L.ptr(gamma), L.ptr(beta), L.ptr(partial), partial.shape[1],
+                                                      L.ptr(ws), B, T, C, eps, L.dtype_code(x.dtype), L.stream_ptr()),
+            "groupnorm_relu_partial")
     return x
 
 

@@ -46,7 +46,9 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
     """sizeof / offsetof of the two ABI structs as gcc lays them out from include/styler_b200.h == the ctypes mirrors."""
     import ctypes
     from styler_b200 import _lib
-    structs = {"styler_conv1d_args": _lib.Conv1dArgs, "styler_fft_weights": _lib.FftWeights}
+    structs = {"styler_conv1d_args": _lib.Conv1dArgs, "styler_fft_weights": _lib.FftWeights,
+               "styler_predictor_weights": _lib.PredictorWeights, "styler_postnet_weights": _lib.PostnetWeights,
+               "styler_decoder_weights": _lib.DecoderWeights}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "styler_b200.h"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
