@@ -85,24 +85,26 @@ class Engine:
         self._pack({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
 
     # ------------------------------------------------------------------------------------------ packing
+    # Packing runs on the HOST (permutes, folds, casts), each packed tensor then crosses to the device as one memcpy: model
+    # load launches no ATen kernels on the GPU (round 1: ~180 copy / cat launches per load).
     def _f32(self, t):
-        return t.detach().to(self.device, torch.float32).contiguous()
+        return t.detach().to("cpu", torch.float32).contiguous().to(self.device)
 
     def _w(self, t):
         """Conv1d weight [N,Cin,KS] (or Linear [N,Cin]) -> [KS,N,Cin] in the activation dtype."""
-        t = t.detach().to(self.device, torch.float32)
+        t = t.detach().to("cpu", torch.float32)
         if t.dim() == 2:
             t = t.unsqueeze(-1)
-        return t.permute(2, 0, 1).contiguous().to(self.dt)
+        return t.permute(2, 0, 1).contiguous().to(self.dt).to(self.device)
 
     def _pack_fft(self, sd, p):
         W = _NS()
         a = p + "slf_attn."
         inv_temp = 1.0 / math.sqrt(64.0)   # temperature sqrt(d_k) (SubLayers.py:24); power of two -> exact fold
-        wq = sd[a + "w_qs.weight"].to(self.device, torch.float32) * inv_temp
-        bq = sd[a + "w_qs.bias"].to(self.device, torch.float32) * inv_temp
-        W.wqkv = self._w(torch.cat([wq, sd[a + "w_ks.weight"].to(self.device), sd[a + "w_vs.weight"].to(self.device)], 0))
-        W.bqkv = self._f32(torch.cat([bq, sd[a + "w_ks.bias"].to(self.device), sd[a + "w_vs.bias"].to(self.device)], 0))
+        wq = sd[a + "w_qs.weight"].float() * inv_temp
+        bq = sd[a + "w_qs.bias"].float() * inv_temp
+        W.wqkv = self._w(torch.cat([wq, sd[a + "w_ks.weight"].float(), sd[a + "w_vs.weight"].float()], 0))
+        W.bqkv = self._f32(torch.cat([bq, sd[a + "w_ks.bias"].float(), sd[a + "w_vs.bias"].float()], 0))
         W.wfc, W.bfc = self._w(sd[a + "fc.weight"]), self._f32(sd[a + "fc.bias"])
         W.ln1 = (self._f32(sd[a + "layer_norm.weight"]), self._f32(sd[a + "layer_norm.bias"]))
         f = p + "pos_ffn."
@@ -127,6 +129,7 @@ class Engine:
 
     def _pack(self, sd):
         P, SE = "style_modeling.", "style_modeling.style_encoder."
+        sd = {k: v.detach().to("cpu") for k, v in sd.items()}        # one D2H per tensor if the parameters live on the GPU
         w = _NS()
         te = SE + "text_encoder."
         w.emb = self._f32(sd[te + "src_word_emb.weight"])
@@ -187,9 +190,9 @@ class Engine:
         for j in range(5 if "postnet.convolutions.0.0.conv.weight" in sd else 0):   # (absent when use_postnet=False, styler.py:24-26)
             # fold eval-mode BatchNorm1d into the conv (Layers.py:91-119,121-130)
             q = "postnet.convolutions.%d." % j
-            cw, cb = sd[q + "0.conv.weight"].to(self.device, torch.float32), sd[q + "0.conv.bias"].to(self.device, torch.float32)
-            g, be = sd[q + "1.weight"].to(self.device, torch.float32), sd[q + "1.bias"].to(self.device, torch.float32)
-            rm, rv = sd[q + "1.running_mean"].to(self.device, torch.float32), sd[q + "1.running_var"].to(self.device, torch.float32)
+            cw, cb = sd[q + "0.conv.weight"].float(), sd[q + "0.conv.bias"].float()
+            g, be = sd[q + "1.weight"].float(), sd[q + "1.bias"].float()
+            rm, rv = sd[q + "1.running_mean"].float(), sd[q + "1.running_var"].float()
             scale = g / torch.sqrt(rv + 1e-5)
             w.postnet.append((self._w(cw * scale[:, None, None]), self._f32((cb - rm) * scale + be)))
         w.dec_struct = ops.make_decoder_weights([W.c_struct for W in w.dec_layers], w.mel[0], w.mel[1], w.postnet)
