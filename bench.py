@@ -116,6 +116,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist) BEFORE it allocates pinned host memory, so the step's
+    H2D / D2H DMA does not cross the socket interconnect (8 ranks x 127 MB per step otherwise converge on one socket)."""
+    try:
+        prop = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        cpus = set()
+        for part in open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return sorted(allowed)[:2] + ["..."] + [len(allowed)]
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
     """Threads the CPU arm may really use: affinity mask and cgroup CPU quota (a 128-CPU box with a small quota
     collapses under 128 torch threads), capped at 32 (the forward stops scaling beyond that)."""
@@ -273,6 +292,68 @@ def _flush_buffer(dev):
     return torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > the 126 MB L2
 
 
+def cpu_fftblock(B=16, Ln=128):
+    """Oracle port (torch CPU fp32) of the configs[1] FFT-block call on the host threads."""
+    from oracle import styler_oracle as so       # CPU-baseline leg only
+    from styler_b200 import synthetic as syn
+    torch.set_num_threads(host_threads())
+    sd = syn.make_state_dict(2)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, Ln, 256, generator=g)
+    lens = torch.randint(64, Ln + 1, (B,), generator=g)
+    lens[0] = Ln
+    mask = so.mask_from_lengths(lens, Ln)
+    x = x.masked_fill(mask.unsqueeze(-1), 0)
+    with torch.no_grad():
+        so.fft_block(sd, "decoder.layer_stack.2.", x, mask)
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            so.fft_block(sd, "decoder.layer_stack.2.", x, mask)
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": B * Ln / dt, "unit": "tokens/s", "cores": host_threads(), "kind": "port",
+            "sample": "oracle port (torch CPU fp32) of the same FFT block call, mean of %d (%.1f ms each)" % (reps, dt * 1e3)}, dt
+
+
+def cpu_stft(y_host, F, cb=32):
+    """Oracle port of the reference's dense conv-DFT mel path (audio/stft.py:51-79) on a bounded sample of the same utterances."""
+    from oracle import stft_oracle               # CPU-baseline leg only
+    torch.set_num_threads(host_threads())
+    yc = y_host[:cb].clone()
+    with torch.no_grad():
+        stft_oracle.mel_spectrogram(yc, dense=True)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            stft_oracle.mel_spectrogram(yc, dense=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return {"value": cb * F / best, "unit": "STFT frames/s", "cores": host_threads(), "kind": "port",
+            "sample": "oracle port of the reference's dense conv-DFT path (audio/stft.py:51-79), B=%d of the same 4 s utterances, "
+                      "best of 3 (%.2f s each)" % (cb, best)}, best
+
+
+def run_reference_side(args):
+    """`--impl reference` for the secondary workloads: the CPU arm alone, same JSON keys."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if args.workload == "fftblock":
+        cpu, dt = cpu_fftblock()
+        metric, unit, wl = "tokens/sec (one FFTBlock: attention + Conv1d FFN)", "tokens/s", "BASELINE configs[1]: one FFTBlock, B=16, L=128, fp32 (CPU oracle port)"
+    elif args.workload == "stft":
+        g = torch.Generator().manual_seed(5)
+        y = (torch.rand(32, 88200, generator=g) * 2 - 1) * 0.5
+        cpu, dt = cpu_stft(y, 1 + 88200 // 256)
+        metric, unit, wl = "STFT frames/sec (TacotronSTFT mel extraction)", "STFT frames/s", "BASELINE configs[3] sample: B=32 x 4 s utterances (CPU oracle port)"
+    else:
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for workload %s" % args.workload}))
+        return
+    print(json.dumps({"impl": "reference", "metric": metric, "value": cpu["value"], "unit": unit, "n_gpus": args.gpus, "steps": 1,
+                      "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": {"workload": wl}, "cpu_baseline": cpu,
+                      "e2e": {"value": cpu["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
 def run_fftblock(args):
     """BASELINE configs[1]: ONE FFTBlock (attention + Conv1d FFN, transformer/Layers.py:26-34) at B=16, L=128, fp32 I/O --
     the fp32-parity tensor-core mode (tcgen05 kind::tf32, fp32 storage) unless --precision bf16.  tokens/s; L2 flushed
@@ -339,20 +420,7 @@ def run_fftblock(args):
                  "achieved": ach, "unit": "TFLOP/s", "flops_per_launch": flops, "traffic": None,
                  "note": "2048 tokens = 16 M-tiles of 128: far too small to fill 148 SMs; launch latency and tile quantisation bound it"},
                 **tensor_roofline(ach, peaks, ck, 0.5 if precision == "tf32" else 1.0))
-    cpu = None
-    if not args.no_cpu_baseline:
-        from oracle import styler_oracle as so       # CPU-baseline leg only
-        torch.set_num_threads(host_threads())
-        xm, mask = x_host.clone(), so.mask_from_lengths(lens, Ln)
-        with torch.no_grad():
-            so.fft_block(sd, "decoder.layer_stack.2.", xm, mask)
-            t0 = time.perf_counter()
-            reps = 20
-            for _ in range(reps):
-                so.fft_block(sd, "decoder.layer_stack.2.", xm, mask)
-            dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": B * Ln / dt, "unit": "tokens/s", "cores": host_threads(), "kind": "port",
-               "sample": "oracle port (torch CPU fp32) of the same FFT block call, mean of %d (%.1f ms each)" % (reps, dt * 1e3)}
+    cpu = None if args.no_cpu_baseline else cpu_fftblock(B, Ln)[0]
     print(json.dumps({
         "metric": "tokens/sec (one FFTBlock: attention + Conv1d FFN)", "value": B * Ln / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -425,23 +493,7 @@ def run_stft(args):
             "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "peak_source": peaks["src"] + " hbm_gbs",
             "bytes_per_launch": nbytes, "traffic": traffic,
             "note": "HBM is the contractual bound (SURVEY.md 8(d)); the FFT stage is ALU/issue work, see profiles/"}
-    cpu = None
-    if not args.no_cpu_baseline:
-        from oracle import stft_oracle               # CPU-baseline leg only
-        torch.set_num_threads(host_threads())
-        cb = 32
-        yc = y_host[:cb].clone()
-        with torch.no_grad():
-            stft_oracle.mel_spectrogram(yc, dense=True)
-            best = None
-            for _ in range(3):
-                t0 = time.perf_counter()
-                stft_oracle.mel_spectrogram(yc, dense=True)
-                dt = time.perf_counter() - t0
-                best = dt if best is None else min(best, dt)
-        cpu = {"value": cb * F / best, "unit": "STFT frames/s", "cores": host_threads(), "kind": "port",
-               "sample": "oracle port of the reference's dense conv-DFT path (audio/stft.py:51-79), B=%d of the same 4 s utterances, "
-                         "best of 3 (%.2f s each)" % (cb, best)}
+    cpu = None if args.no_cpu_baseline else cpu_stft(y_host, F)[0]
     print(json.dumps({
         "metric": "STFT frames/sec (TacotronSTFT mel extraction)", "value": B * F / (ms * 1e-3), "unit": "STFT frames/s", "n_gpus": 1,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -464,15 +516,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every forward kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true", help="skip the tf32 and B=1 latency side measurements")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: peer = the producing kernels store the mels straight into rank 0's IPC-mapped buffer over NVLink "
-                         "(fused compute + gather, dist.PeerGather); nccl = one packed NCCL gather per step")
+    ap.add_argument("--gather", default="push", choices=["push", "peer", "nccl"],
+                    help="N > 1, how the mels reach rank 0: push = DMA copy of the packed results into rank 0's IPC-mapped region on a "
+                         "side stream + our flag protocol (overlaps the next step, no SM time); peer = FUSED, the producing kernels store "
+                         "into that region from their epilogues; nccl = one packed NCCL gather per step")
     ap.add_argument("--workload", default="styler", choices=["styler", "vocoder", "fftblock", "stft"],
                     help="styler = BASELINE.json's headline metric, configs[2] (default); fftblock = configs[1]; stft = configs[3]; "
                          "vocoder = secondary HiFi-GAN line (all but styler: single GPU)")
     args = ap.parse_args()
     args.precision_given = args.precision is not None
     args.precision = args.precision or "bf16"
+    if args.impl == "reference" and args.workload != "styler":
+        run_reference_side(args)
+        return
     if args.workload == "vocoder":
         args.steps = min(args.steps, 10)
         run_vocoder(args)
@@ -496,6 +552,7 @@ def main():
     from styler_b200 import STYLER, GraphedSTYLER, _lib
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     model = STYLER(precision=args.precision)
     model.load_state_dict(so.make_state_dict(0))
     model = model.to(dev).eval()
@@ -522,10 +579,11 @@ def main():
     # the other graph.
     use_graph = not args.no_graph
     from styler_b200.engine import packed_nbytes
-    peer = world > 1 and args.gather == "peer"
+    peer = world > 1 and args.gather == "peer"          # fused: the forward itself writes rank 0's memory
+    push = world > 1 and args.gather == "push"
     gatherer = None
     if world > 1:
-        gatherer = sdist.AsyncPeerGather(dev, packed_nbytes(B_PER_GPU, T)) if peer else sdist.AsyncGather(dev)
+        gatherer = sdist.AsyncPeerGather(dev, packed_nbytes(B_PER_GPU, T), push=push) if (peer or push) else sdist.AsyncGather(dev)
     for i in range(args.warmup):                    # eager warm-up: engine build, position tables, allocator pools
         model(*split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
     torch.cuda.synchronize()
@@ -538,7 +596,7 @@ def main():
 
     def step(bt, slot):
         a, kw = split(bt) if bt is not None else ((), {})      # bt None: the inputs already sit in graph `slot`'s static buffers
-        if peer:
+        if peer or push:
             gatherer.begin(slot)                     # flow control: rank 0 has consumed the previous contents of this slot
         elif gatherer is not None and use_graph:
             gatherer.before_reuse(slot)              # the previous gather out of this graph's static outputs has drained
@@ -746,7 +804,7 @@ def main():
                                                     "wall clock per call incl. synchronize; eager has one host read of max(mel_len)"}
         del g1, m1
 
-    if peer:
+    if peer or push:
         torch.cuda.synchronize()
         gatherer.close()
     if rank != 0:
@@ -772,6 +830,8 @@ def main():
                    "gather": ("none (N=1)" if world == 1 else
                               ("fused compute+gather: mel_linear / last PostNet conv store into rank 0's IPC-mapped buffer over NVLink "
                                "(%d bytes/rank/step), flag protocol; inside the timed events" if peer else
+                               "DMA push of the packed results (%d bytes/rank/step) into rank 0's IPC-mapped buffer on a side stream + flag "
+                               "protocol; inside the timed events" if push else
                                "one packed NCCL gather per step (4 fp32 mels + lengths, %d bytes/rank), inside the timed events")
                               % packed_nbytes(B_PER_GPU, T)),
                    "l2": "inputs rotate over %d resident batches (> L2); per-step activations >> L2; no explicit flush" % NBUF},
@@ -779,7 +839,7 @@ def main():
                 "ms_per_step": 1e3 * e2e_secs / args.steps,
                 "what": "pinned host inputs -> H2D -> forward -> D2H of all four mel tensors + lengths, every step"},
         "gpu_launches": launches, "launches_per_step": launches_per_step, "clocks": ck, "roofline": roof, "cpu_baseline": cpu,
-        "wall_s_timed_region": wall, "host_enqueue_ms_per_step": 1e3 * enqueue[0], "extras": extras or None}))
+        "wall_s_timed_region": wall, "host_enqueue_ms_per_step": 1e3 * enqueue[0], "cpu_binding": numa, "extras": extras or None}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

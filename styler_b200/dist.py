@@ -293,11 +293,19 @@ class AsyncPeerGather:
         g.wait()                       # join the side stream (end of a timed region / before reading `result`)
     """
 
-    def __init__(self, device, nbytes, slots=2, dst=0):
+    def __init__(self, device, nbytes, slots=2, dst=0, push=False):
+        """push=False: FUSED -- the producing kernels store into the peer region (engine.result_mirror = buffer(slot)).
+        push=True: the forward writes its local packed buffer only; `launch_packed(packed, slot)` then pushes it into the peer
+        region on the side stream with one DMA copy (copy engine over NVLink, no SM time) and publishes the flag behind it, so
+        the transfer overlaps the next step.  (Measured at N = 8: the fused stores of all ranks converge on rank 0's NVLink
+        ingress at the END of every step -- 588 MB, ~0.8 ms, on the critical path; pushed or gathered asynchronously the
+        same bytes hide under the next step's 7 ms of compute.)"""
         self.pg = PeerGather(device, nbytes, slots, dst)
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.push = bool(push)
         self._done = {}
+        self._bufs = {}
         self.result = None
 
     def buffer(self, slot):
@@ -309,12 +317,35 @@ class AsyncPeerGather:
 
     def begin(self, slot):
         self.before_reuse(slot)
-        self.pg.begin(slot)
+        if self.push:            # the ack wait belongs in front of the COPY (side stream), not in front of the forward
+            with torch.cuda.stream(self.stream):
+                self.pg.begin(slot)
+        else:
+            self.pg.begin(slot)
 
     def launch_packed(self, packed, slot=0):
+        main = torch.cuda.current_stream(self.device)
+        if self.push:
+            # side stream: [wait for the forward] -> DMA copy local packed -> this rank's slice of rank 0's region -> flag
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self.stream.wait_event(ready)
+            with torch.cuda.stream(self.stream):
+                packed.record_stream(self.stream)
+                if slot not in self._bufs:
+                    self._bufs[slot] = self.pg.buffer(slot)
+                self._bufs[slot].copy_(packed, non_blocking=True)
+                self.pg.commit(slot)
+                if not self.pg.remote:
+                    self.result = self.pg.collect(slot)
+                    self.pg.release(slot)
+                ev = self._done.get(slot)
+                if ev is None:
+                    ev = self._done[slot] = torch.cuda.Event()
+                ev.record(self.stream)
+            return
         self.pg.commit(slot)
         if not self.pg.remote:
-            main = torch.cuda.current_stream(self.device)
             ready = torch.cuda.Event()
             ready.record(main)
             self.stream.wait_event(ready)

@@ -65,6 +65,26 @@ for step in range(7):
                 print("MISMATCH step", step, "rank", r, (got[r] != bufs[r]).sum().item())
     dist.barrier()
 g.close()
+# push mode: the forward writes only its local packed buffer; a DMA copy on the side stream carries it into rank 0's region
+g2 = sdist.AsyncPeerGather(dev, nb, slots=2, push=True)
+for step in range(5):
+    slot = step %% 2
+    a, kw = batch(5000 * step + rank)
+    g2.begin(slot)
+    model(*a, **kw)
+    local_packed = eng.last_packed
+    g2.launch_packed(local_packed, slot)
+    bufs = [torch.empty_like(local_packed) for _ in range(world)] if rank == 0 else None
+    dist.gather(local_packed, bufs, dst=0)
+    if rank == 0:
+        got = g2.wait()
+        torch.cuda.synchronize()
+        for r in range(world):
+            if not torch.equal(got[r], bufs[r]):
+                ok = False
+                print("PUSH MISMATCH step", step, "rank", r)
+    dist.barrier()
+g2.close()
 if rank == 0:
     print("PEER_GATHER_OK" if ok else "PEER_GATHER_BAD")
 dist.destroy_process_group()
