@@ -705,11 +705,14 @@ def main():
     d2h = [torch.empty(packed_nbytes(B_PER_GPU, T), dtype=torch.uint8).pin_memory() for _ in range(2)]
 
     compute_done = [None]                              # event after the previous step's kernels
+    diag = os.environ.get("STYLER_BENCH_E2E_DIAG", "")  # diagnostic runs only: "noh2d" / "nod2h" drop one copy direction
 
     def e2e_step(i):
         k = i % 2
         with torch.cuda.stream(e2e_streams[k]):
             hb = host[i % NBUF]
+            if "noh2d" in diag:
+                hb = resident[i % NBUF]
             if use_graph:                              # H2D of the (pinned host) inputs straight into graph k's static buffers
                 graphs[k].load_inputs(*split(hb)[0], **split(hb)[1])
             else:
@@ -727,7 +730,8 @@ def main():
             ev = torch.cuda.Event()
             ev.record(e2e_streams[k])
             compute_done[0] = ev
-            d2h[k].copy_(packed, non_blocking=True)
+            if "nod2h" not in diag:
+                d2h[k].copy_(packed, non_blocking=True)
 
     def e2e_timed(steps):
         barrier()
@@ -837,7 +841,8 @@ def main():
                    "l2": "inputs rotate over %d resident batches (> L2); per-step activations >> L2; no explicit flush" % NBUF},
         "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_secs / args.steps,
-                "what": "pinned host inputs -> H2D -> forward -> D2H of all four mel tensors + lengths, every step"},
+                "what": "pinned host inputs -> H2D -> forward -> D2H of all four mel tensors + lengths, every step" +
+                        (" [DIAGNOSTIC RUN %s: not an e2e number]" % diag if diag else "")},
         "gpu_launches": launches, "launches_per_step": launches_per_step, "clocks": ck, "roofline": roof, "cpu_baseline": cpu,
         "wall_s_timed_region": wall, "host_enqueue_ms_per_step": 1e3 * enqueue[0], "cpu_binding": numa, "extras": extras or None}))
     if world > 1:

@@ -310,26 +310,56 @@ __global__ void mel_calibrator_kernel(const T* __restrict__ x, long long x_bs, i
 }
 
 // ---------------------------------------------------------------------------------------- classifier tail
+// One CTA per utterance, one warp per row (4 rows in flight per warp): every lane holds 8 consecutive channels of the two
+// weight rows in registers and reads its 8 activations with one 16-byte load.  (Round 1 read 2-byte elements one at a
+// time and re-read the weights from global for every row: 40 us for a 64-CTA toy op.)
 template <typename T>
 __global__ void __launch_bounds__(256) classifier_tail_kernel(const T* __restrict__ h, long long h_bs, int h_ld,
                                                               const float* __restrict__ w, const float* __restrict__ bias,
                                                               float* __restrict__ out, int L, int C) {
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float b0 = bias[0], b1 = bias[1];
   float a0 = 0.f, a1 = 0.f;
-  for (int l = warp; l < L; l += 8) {
-    const T* row = h + b * h_bs + static_cast<long long>(l) * h_ld;
-    float z0 = 0.f, z1 = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float v = DT<T>::ld(row + c);
-      z0 = fmaf(v, w[c], z0);
-      z1 = fmaf(v, w[C + c], z1);
-    }
-    z0 = warp_sum(z0) + bias[0];
-    z1 = warp_sum(z1) + bias[1];
+  auto finish_row = [&](float z0, float z1) {
+    z0 = warp_sum(z0) + b0;
+    z1 = warp_sum(z1) + b1;
     const float m = fmaxf(z0, z1);
     const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
     a0 += z0 - lse;
     a1 += z1 - lse;
+  };
+  if (C == 256) {
+    float w0[8], w1[8];
+    load8(w + lane * 8, w0);
+    load8(w + C + lane * 8, w1);
+    constexpr int U = 4;
+    for (int l0 = warp; l0 < L; l0 += 8 * U) {
+      float v[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int l = l0 + 8 * u;
+        if (l < L) load8(h + b * h_bs + static_cast<long long>(l) * h_ld + lane * 8, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (l0 + 8 * u >= L) break;       // warp-uniform
+        float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { z0 = fmaf(v[u][i], w0[i], z0); z1 = fmaf(v[u][i], w1[i], z1); }
+        finish_row(z0, z1);
+      }
+    }
+  } else {
+    for (int l = warp; l < L; l += 8) {
+      const T* row = h + b * h_bs + static_cast<long long>(l) * h_ld;
+      float z0 = 0.f, z1 = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float v = DT<T>::ld(row + c);
+        z0 = fmaf(v, w[c], z0);
+        z1 = fmaf(v, w[C + c], z1);
+      }
+      finish_row(z0, z1);
+    }
   }
   __shared__ float s0[8], s1[8];
   if (lane == 0) { s0[warp] = a0; s1[warp] = a1; }
@@ -605,6 +635,7 @@ extern "C" int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32
 extern "C" int styler_classifier_tail_fwd(const void* h, int64_t h_bstride, int32_t h_ld, const float* w, const float* b,
                                           float* out, int32_t B, int32_t L, int32_t C, int32_t dtype, void* stream) {
   SB_REQUIRE(h && w && b && out && B > 0 && L > 0 && C > 0, "classifier_tail: bad arguments");
+  SB_REQUIRE(C != 256 || (al16(h) && h_ld % 8 == 0 && h_bstride % 8 == 0 && al16(w)), "classifier_tail: rows must be 16-byte aligned");
   SB_DISPATCH_DTYPE(dtype, TT, (classifier_tail_kernel<TT><<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
                                    static_cast<const TT*>(h), h_bstride, h_ld, w, b, out, L, C)));
   SB_LAUNCH_OK();

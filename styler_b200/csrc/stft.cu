@@ -41,12 +41,16 @@ __device__ __forceinline__ float sqrt_approx(float x) {   // MUFU.SQRT (2 ulp): 
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-  return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+// Complex arithmetic on packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: one issue slot per COMPLEX add, two per complex
+// multiply).  ptxas folds the component swaps and sign flips below into operand modifiers (.F32 broadcast, .F32x2.LO_HI, .NP):
+// no register moves.  The scalar round-1 kernel spent 57 % of its 2.1 k warp-instructions per frame on FADD/FMUL/FFMA.
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {       // (a.x w.x - a.y w.y, a.x w.y + a.y w.x)
+  const float2 t = __fmul2_rn(make_float2(a.x, a.x), w);
+  return __ffma2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x), t);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i): folded into the consumer
 
 // 4-point forward DFT, natural order in and out
 __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
@@ -58,9 +62,9 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   constexpr float kR = 0.70710678118654752f;
   float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
   float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
-  b1 = make_float2((b1.x + b1.y) * kR, (b1.y - b1.x) * kR);      // * (1 - i)/sqrt(2)
+  b1 = __fmul2_rn(cadd(b1, mul_mi(b1)), make_float2(kR, kR));        // * (1 - i)/sqrt(2):  ((x + y) r, (y - x) r)
   b2 = mul_mi(b2);
-  b3 = make_float2((b3.y - b3.x) * kR, -(b3.x + b3.y) * kR);     // * (-1 - i)/sqrt(2)
+  b3 = __fmul2_rn(csub(b3, mul_mi(b3)), make_float2(-kR, -kR));      // * (-1 - i)/sqrt(2): ((y - x) r, -(x + y) r)
   dft4(a0, a1, a2, a3);
   dft4(b0, b1, b2, b3);
   v[0] = a0; v[1] = b0; v[2] = a1; v[3] = b1; v[4] = a2; v[5] = b2; v[6] = a3; v[7] = b3;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
           // periodic Hann: 0.5 - 0.5 cos(2 pi i / 1024), cos(2 pi i / 1024) = Re W^i = -Re W^(i-512)
           const float4 c = tw2[n & (HALF / 2 - 1)];
           const float sg = n < HALF / 2 ? -0.5f : 0.5f;
-          v[u][r] = make_float2(x.x * fmaf(sg, c.x, 0.5f), x.y * fmaf(sg, c.z, 0.5f));
+          v[u][r] = __fmul2_rn(x, __ffma2_rn(make_float2(sg, sg), make_float2(c.x, c.z), make_float2(0.5f, 0.5f)));
         }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -226,12 +230,14 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
     for (int k = lane; k <= HALF / 2; k += 32) {
       const float2 zk = wb[slot(k & (HALF - 1))];
       const float2 zr = wb[slot((HALF - k) & (HALF - 1))];
-      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
-      const float2 o = make_float2(0.5f * (zk.y + zr.y), -0.5f * (zk.x - zr.x));        // -i/2 * (zk - conj(zr))
+      const float2 zc = make_float2(zr.x, -zr.y);                                        // conj(Z[512-k])
+      const float2 e = __fmul2_rn(cadd(zk, zc), make_float2(0.5f, 0.5f));                // E(k)
+      const float2 o = __fmul2_rn(mul_mi(csub(zk, zc)), make_float2(0.5f, 0.5f));        // O(k) = -i/2 (Z[k] - conj(Z[512-k]))
       const float2 wo = cmul(o, tw[k]);
-      const float xr = e.x + wo.x, xi = e.y + wo.y;                                      // X[k]
-      const float yr = e.x - wo.x, yi = -e.y + wo.y;                                     // X[512-k] = conj(E) - conj(W^k O)
-      const float p0 = xr * xr + xi * xi, p1 = yr * yr + yi * yi;
+      const float2 X = cadd(e, wo);                                                      // X[k]
+      const float2 Y = __fadd2_rn(make_float2(e.x, -e.y), make_float2(-wo.x, wo.y));     // X[512-k] = conj(E) - conj(W^k O)
+      const float2 pp = __ffma2_rn(make_float2(X.y, Y.y), make_float2(X.y, Y.y), __fmul2_rn(make_float2(X.x, Y.x), make_float2(X.x, Y.x)));
+      const float p0 = pp.x, p1 = pp.y;
       mg[k] = sqrt_approx(p0);
       mg[HALF - k] = sqrt_approx(p1);
       esum += k == HALF / 2 ? p0 : p0 + p1;     // bin 256 is its own mirror
