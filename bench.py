@@ -512,7 +512,10 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=None, choices=["bf16", "tf32"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "tf32"])
+    ap.add_argument("--pipeline", type=int, default=0, choices=[0, 1],
+                    help="1: two-stage software pipeline over consecutive batches (model.PipelinedSTYLER): stage one (style encoders + "
+                         "variance adaptor) of batch i+1 runs on a low-priority stream under stage two (decoder + PostNet) of batch i")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every forward kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true", help="skip the tf32 and B=1 latency side measurements")
@@ -549,7 +552,7 @@ def main():
 
     import torch.distributed as dist
     from styler_b200 import synthetic as so      # seeded synthetic weights/inputs (no oracle import on the GPU arm)
-    from styler_b200 import STYLER, GraphedSTYLER, _lib
+    from styler_b200 import STYLER, GraphedSTYLER, PipelinedSTYLER, _lib
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     numa = bind_to_gpu_numa(local) if world > 1 else None
@@ -578,6 +581,9 @@ def main():
     # so the gather (N > 1) or the D2H copies (e2e) of step i can still be reading graph k's outputs while step i+1 runs in
     # the other graph.
     use_graph = not args.no_graph
+    LAUNCH_DESC = ("two-stage batch pipeline (PipelinedSTYLER): per slot one CUDA graph for style encoders + variance adaptor on a "
+                   "low-priority stream and one for decoder + PostNet on a high-priority stream; stage one of batch i+1 overlaps stage "
+                   "two of batch i; 2 slots" if args.pipeline else "CUDA-graph replay of the forward (2 alternating graphs)")
     from styler_b200.engine import packed_nbytes
     peer = world > 1 and args.gather == "peer"          # fused: the forward itself writes rank 0's memory
     push = world > 1 and args.gather == "push"
@@ -588,7 +594,13 @@ def main():
         model(*split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
     torch.cuda.synchronize()
     graphs = []
-    if use_graph:
+    pipe = None
+    d2h_done = [None, None]                          # e2e: event behind the D2H copy that still reads slot k's results
+    if use_graph and args.pipeline:
+        a0, k0 = split(resident[0])
+        pipe = PipelinedSTYLER(model, a0, k0, slots=2, result_mirrors=[gatherer.buffer(k) for k in range(2)] if peer else None,
+                               back_priority=int(os.environ.get("STYLER_PIPE_PRIO", "-1")))
+    elif use_graph:
         a0, k0 = split(resident[0])
         # peer gather: graph k is captured with this rank's slice (slot k) of rank 0's receive region as the second destination
         # of mel_linear / the last PostNet conv -- the NVLink stores are part of the captured kernels
@@ -596,6 +608,22 @@ def main():
 
     def step(bt, slot):
         a, kw = split(bt) if bt is not None else ((), {})      # bt None: the inputs already sit in graph `slot`'s static buffers
+        if pipe is not None:
+            if bt is not None:
+                pipe.load_inputs(slot, *a, **kw)
+
+            def pre():                                # (stage-two stream current) flow control of the gather
+                if peer or push:
+                    gatherer.begin(slot)
+                elif gatherer is not None:
+                    gatherer.before_reuse(slot)
+
+            def post():
+                if gatherer is not None:
+                    gatherer.launch_packed(pipe.packed[slot], slot)
+
+            pipe.run(slot, after=(d2h_done[slot],), pre_back=pre, post_back=post)
+            return pipe.outputs(slot)
         if peer or push:
             gatherer.begin(slot)                     # flow control: rank 0 has consumed the previous contents of this slot
         elif gatherer is not None and use_graph:
@@ -631,6 +659,8 @@ def main():
             fn(i)
             if i == min(3, steps) - 1:               # host time per step while the launch queue is still empty: later steps
                 enqueue[0] = (time.perf_counter() - t0) / (i + 1)   # are throttled by queue back-pressure to the device pace
+        if pipe is not None:
+            pipe.join()                              # both pipeline streams are joined into the timed stream before e1
         if gatherer is not None:
             gatherer.wait()                          # the timed events cover the gathers: join the comm stream before e1
         e1.record()
@@ -707,7 +737,21 @@ def main():
     compute_done = [None]                              # event after the previous step's kernels
     diag = os.environ.get("STYLER_BENCH_E2E_DIAG", "")  # diagnostic runs only: "noh2d" / "nod2h" drop one copy direction
 
+    def e2e_step_pipe(i):
+        k = i % 2
+        with torch.cuda.stream(e2e_streams[k]):       # copy stream of slot k: H2D -> (pipeline streams: both stages) -> D2H
+            hb = host[i % NBUF]
+            pipe.load_inputs(k, *split(hb)[0], **split(hb)[1])
+            step(None, k)
+            e2e_streams[k].wait_event(pipe.done(k))
+            d2h[k].copy_(pipe.packed[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(e2e_streams[k])
+            d2h_done[k] = ev
+
     def e2e_step(i):
+        if pipe is not None:
+            return e2e_step_pipe(i)
         k = i % 2
         with torch.cuda.stream(e2e_streams[k]):
             hb = host[i % NBUF]
@@ -742,6 +786,8 @@ def main():
             e2e_step(i)
         for st in e2e_streams:
             st.synchronize()
+        if pipe is not None:
+            pipe.s_back.synchronize()
         barrier()
         wall = time.perf_counter() - t0
         tt = torch.tensor([wall], device=dev)
@@ -760,27 +806,33 @@ def main():
     if world == 1 and not args.no_extras:
         torch.cuda.synchronize()
         del graphs[:]
-        other = "tf32" if args.precision == "bf16" else "bf16"
-        m2 = STYLER(precision=other)
-        m2.load_state_dict(so.make_state_dict(0))
-        m2 = m2.to(dev).eval()
-        a0, k0 = split(resident[0])
-        for _ in range(3):
-            m2(*a0, **k0)
-        torch.cuda.synchronize()
-        n2 = min(args.steps, 10)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(n2):
-            a, kw = split(resident[i % NBUF])
-            m2(*a, **kw)
-        e1.record()
-        torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / n2
-        extras[other + "_same_workload"] = {"ms_per_step": ms2, "value": frames_per_step / (ms2 * 1e-3), "unit": "mel-frames/s",
-                                            "steps": n2, "note": "device-resident, eager launches; tf32 = fp32 storage + tcgen05 kind::tf32, "
-                                                                 "the mode that meets the 1e-3 fp32 tolerance"}
-        del m2
+        pipe = None
+        for other in [m_ for m_ in ("fp16", "tf32", "bf16") if m_ != args.precision]:
+            m2 = STYLER(precision=other)
+            m2.load_state_dict(so.make_state_dict(0))
+            m2 = m2.to(dev).eval()
+            a0, k0 = split(resident[0])
+            for _ in range(3):
+                m2(*a0, **k0)
+            torch.cuda.synchronize()
+            n2 = min(args.steps, 10)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n2):
+                a, kw = split(resident[i % NBUF])
+                m2(*a, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / n2
+            extras[other + "_same_workload"] = {
+                "ms_per_step": ms2, "value": frames_per_step / (ms2 * 1e-3), "unit": "mel-frames/s", "steps": n2,
+                "note": "device-resident, eager launches, no batch pipelining; " +
+                        {"tf32": "fp32 storage + tcgen05 kind::tf32; meets the 1e-3 fp32 tolerance on the mels",
+                         "fp16": "IEEE-half storage + tcgen05 kind::f16 (the bf16 kernels, 11-bit significand); meets the 1e-3 fp32 "
+                                 "tolerance on the mels (tests/test_forward_gpu.py, same gates as tf32)",
+                         "bf16": "bf16 storage + tcgen05 kind::f16"}[other]}
+            del m2
+            torch.cuda.empty_cache()
         # BASELINE configs[0]: single utterance, 50 phonemes, free-running durations (8 frames/phoneme via the duration bias)
         sd1 = so.set_duration_bias(so.make_state_dict(0), FRAMES)
         m1 = STYLER(precision=args.precision)
@@ -830,7 +882,7 @@ def main():
                                "(teacher-forced %d frames/phoneme), ref mel %d frames, 80-bin, %s compute; random-init weights"
                                % (B_PER_GPU, L, T, FRAMES, T, args.precision),
                    "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world,
-                   "launch": "CUDA-graph replay of the forward (2 alternating graphs)" if use_graph else "eager kernel launches",
+                   "launch": LAUNCH_DESC if use_graph else "eager kernel launches",
                    "gather": ("none (N=1)" if world == 1 else
                               ("fused compute+gather: mel_linear / last PostNet conv store into rank 0's IPC-mapped buffer over NVLink "
                                "(%d bytes/rank/step), flag protocol; inside the timed events" if peer else

@@ -8,7 +8,7 @@
  *     or frees device memory and keeps no state between calls except a cache of TMA descriptors;
  *   - activations are channel-last [B][T][C]; element (b,t,c) lives at base + b*bstride + t*ld + c (ELEMENTS);
  *   - `dtype` is the activation/weight storage type: STYLER_F32 (tcgen05 kind::tf32 or fp32 SIMT) or
- *     STYLER_BF16 (tcgen05 kind::f16); accumulation, LayerNorm, softmax, LSTM state are always fp32;
+ *     STYLER_BF16 / STYLER_F16 (tcgen05 kind::f16 with bf16 / f16 operands); accumulation, LayerNorm, softmax, LSTM state are always fp32;
  *   - lengths are int64 (as the reference's src_len/mel_len), masks are derived from lengths;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
  *   - return 0 on success, negative = invalid argument, positive = CUDA error code; message via
@@ -24,6 +24,7 @@ extern "C" {
 
 #define STYLER_F32 0
 #define STYLER_BF16 1
+#define STYLER_F16 2 /* IEEE half storage (tcgen05 kind::f16, f16 operands): tf32-class accuracy at the bf16 rate */
 
 #define STYLER_IMPL_AUTO 0
 #define STYLER_IMPL_SIMT 1   /* fp32 CUDA-core kernels (exact-fp32 parity mode, odd shapes) */
@@ -38,6 +39,12 @@ int styler_version(void);
 const char* styler_last_error(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t styler_launch_count(void);
+/* Debug timeline (tools/timeline.py): styler_debug_trace(1) clears and starts recording a CUDA event pair around every leaf
+ * entry point's kernels (also when called from inside a composite entry), (0) stops.  styler_debug_trace_dump synchronises
+ * the device and writes one text line per call -- "name a b c d stream start_ms end_ms", times relative to the first
+ * record -- into buf; returns the bytes needed. */
+int styler_debug_trace(int32_t on);
+int64_t styler_debug_trace_dump(char* buf, int64_t cap);
 
 /* ---- Conv1d / Linear over channel-last activations with fused epilogue ----------------------------------
  * y[b,t,n] = act2( LN( act( sum_{tap,c} x[b,t+tap*dilation-pad,c] * w[tap][n][c] + bias[n] ) + residual[b,t,n] ) )
@@ -62,7 +69,7 @@ typedef struct {
   float* out_f32; int64_t of_bstride; int32_t of_ld;     /* optional fp32 copy of the output or NULL */
   void* vt; int32_t vt_col0; int64_t vt_bstride; int32_t vt_ld; /* optional: columns n >= vt_col0 are stored
                                                             transposed, vt[b][n-vt_col0][t] (dtype), instead of `out` */
-  int32_t dtype;                                         /* STYLER_F32 | STYLER_BF16 */
+  int32_t dtype;                                         /* STYLER_F32 | STYLER_BF16 | STYLER_F16 */
   int32_t impl;                                          /* STYLER_IMPL_* */
   int32_t dilation;                                      /* tap spacing in time steps; 0 or 1 = dense (nn.Conv1d dilation) */
   float act_slope;                                       /* negative-side slope of STYLER_ACT_LRELU (act and act2) */

@@ -2,7 +2,7 @@
 and the TacotronSTFT mel front end, behind the reference's Python surface.  See DESIGN.md / INTEGRATION.md."""
 from . import _lib  # noqa: F401
 
-__all__ = ["STYLER", "GraphedSTYLER", "TacotronSTFT", "Generator", "ReferenceFrontEnd", "ops", "hparams"]
+__all__ = ["STYLER", "GraphedSTYLER", "PipelinedSTYLER", "TacotronSTFT", "Generator", "ReferenceFrontEnd", "ops", "hparams"]
 
 
 def __getattr__(name):
@@ -12,6 +12,9 @@ def __getattr__(name):
     if name == "GraphedSTYLER":
         from .model import GraphedSTYLER
         return GraphedSTYLER
+    if name == "PipelinedSTYLER":
+        from .model import PipelinedSTYLER
+        return PipelinedSTYLER
     if name == "TacotronSTFT":
         from .stft import TacotronSTFT
         return TacotronSTFT

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstyler_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 
@@ -108,6 +108,8 @@ _SIGNATURES = {
                                c_f32, c_vp, c_vp],
     "styler_f0_norm_fwd": [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp],
     "styler_debug_set_phase_buffer": [c_vp, c_i32],
+    "styler_debug_trace": [c_i32],
+    "styler_debug_trace_dump": [ctypes.c_char_p, c_i64],
     "styler_set_tuning": [ctypes.c_char_p, c_i32],
     "styler_predictor_workspace_bytes": [c_i32, c_i32, c_i32, c_i32],
     "styler_predictor_fwd": [ctypes.POINTER(PredictorWeights), c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp,
@@ -147,6 +149,7 @@ def lib():
     h.styler_last_error.restype = ctypes.c_char_p
     h.styler_launch_count.restype = ctypes.c_int64
     h.styler_fftblock_workspace_bytes.restype = ctypes.c_int64
+    h.styler_debug_trace_dump.restype = ctypes.c_int64
     for name in ("styler_predictor_workspace_bytes", "styler_postnet_workspace_bytes", "styler_decoder_workspace_bytes"):
         getattr(h, name).restype = ctypes.c_int64
     _lib = h
@@ -173,6 +176,8 @@ def dtype_code(dt):
         return F32
     if dt == torch.bfloat16:
         return BF16
+    if dt == torch.float16:
+        return F16
     raise TypeError("styler_b200: unsupported activation dtype %s" % dt)
 
 

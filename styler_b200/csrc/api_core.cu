@@ -5,6 +5,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -28,14 +29,42 @@ int num_sms() {
   return sms;
 }
 
+// ---- debug timeline -------------------------------------------------------------------------------------------
+namespace {
+struct TraceRec { const char* name; int a, b, c, d; cudaStream_t stream; cudaEvent_t e0, e1; };
+std::atomic<int> g_trace_on{0};
+std::vector<TraceRec> g_trace;
+std::mutex g_trace_mu;
+}  // namespace
+
+TraceScope::TraceScope(const char* name, void* stream, int a, int b, int c, int d) : idx(-1) {
+  if (g_trace_on.load(std::memory_order_relaxed) == 0) return;
+  TraceRec r{name, a, b, c, d, static_cast<cudaStream_t>(stream), nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, r.stream);
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  idx = static_cast<int>(g_trace.size());
+  g_trace.push_back(r);
+}
+TraceScope::~TraceScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  cudaEventRecord(g_trace[idx].e1, g_trace[idx].stream);
+}
+
 namespace {
 struct TuneDef { const char* name; int dflt, lo, hi; };
 // TC_2CTA: CTA pairs for the big bf16 convs (0 off | 1 where it pays | 2 wherever legal: tests);  TC_PERSIST: persistent conv
 // form (0 | 1 two CTAs/SM | 2 also one CTA/SM);  CONV_WIN: window kernel for <= 64-channel convs;  TC_BN / TC_SMEM_KB: tile and
 // pipeline-depth overrides;  PDL: programmatic dependent launch (off: measured 8.71 ms/step with it vs 8.07 without);
-// ATTN_PERSIST: persistent attention CTAs (0 | 1);  TC_WIDE: full-width N tile (two MMAs per k-step) for 256 < N <= 512
+// ATTN_PERSIST: persistent attention CTAs (0 | 1);  TC_WIDE: full-width N tile (two MMAs per k-step) for 256 < N <= 512;
+// LSTM_MULTI: four utterances per BiLSTM CTA for batches >= 16 (0 | 1);  ATTN_POLY: eighths of the softmax exponentials computed
+// by an FMA-pipe polynomial instead of MUFU.EX2 (0 | 2 | 3 | 4; 16-bit operands);  LSTM_MMA: BiLSTM recurrence on mma.sync,
+// sixteen utterances per CTA (16-bit activations, batches >= 8)
 const TuneDef kTune[TUNE_COUNT] = {{"TC_2CTA", 1, 0, 2}, {"TC_PERSIST", 1, 0, 2}, {"CONV_WIN", 1, 0, 1}, {"TC_BN", 0, 0, 256},
-                                   {"TC_SMEM_KB", 113, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}, {"TC_WIDE", 1, 0, 1}};
+                                   {"TC_SMEM_KB", 113, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}, {"TC_WIDE", 1, 0, 1},
+                                   {"LSTM_MULTI", 0, 0, 1}, {"ATTN_POLY", 2, 0, 4},
+                                   {"LSTM_MMA", 1, 0, 1}};
 std::atomic<int> g_tune[TUNE_COUNT];          // 0 = not resolved yet, else value + 1
 }  // namespace
 
@@ -155,6 +184,42 @@ int styler_set_tuning(const char* name, int32_t value) {
   }
   set_error("set_tuning: unknown switch %s", name);
   return -1;
+}
+// Debug timeline: styler_debug_trace(1) clears and starts recording, (0) stops.  styler_debug_trace_dump synchronises the
+// device and writes one text line per leaf call -- "name a b c d stream start_ms end_ms" (times relative to the first record)
+// -- into buf; returns the number of bytes needed (call again with a larger buffer if it exceeds cap).
+int styler_debug_trace(int32_t on) {
+  using namespace sb;
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (on) {
+    for (auto& r : g_trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_trace.clear();
+  }
+  g_trace_on.store(on ? 1 : 0);
+  return 0;
+}
+int64_t styler_debug_trace_dump(char* buf, int64_t cap) {
+  using namespace sb;
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  std::string out;
+  char line[256];
+  for (size_t i = 0; i < g_trace.size(); ++i) {
+    const TraceRec& r = g_trace[i];
+    float t0 = 0.f, t1 = 0.f;
+    if (cudaEventElapsedTime(&t0, g_trace[0].e0, r.e0) != cudaSuccess) t0 = -1.f;
+    if (cudaEventElapsedTime(&t1, g_trace[0].e0, r.e1) != cudaSuccess) t1 = -1.f;
+    snprintf(line, sizeof(line), "%s %d %d %d %d %llu %.4f %.4f\n", r.name, r.a, r.b, r.c, r.d,
+             static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(r.stream)), t0, t1);
+    out += line;
+  }
+  cudaGetLastError();
+  if (buf != nullptr && cap > 0) {
+    const size_t n = out.size() < static_cast<size_t>(cap - 1) ? out.size() : static_cast<size_t>(cap - 1);
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return static_cast<int64_t>(out.size()) + 1;
 }
 int styler_version(void) { return 200; }
 const char* styler_last_error(void) { return sb::g_err; }

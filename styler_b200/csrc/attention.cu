@@ -82,6 +82,24 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2, flush-to-ze
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a PAIR of scores on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x) taken from the low mantissa bits of
+// x + 1.5 * 2^23, 2^f by a degree-3 minimax polynomial on [-0.5, 0.5] (max. relative error 7.5e-5: below the rounding of P to
+// bf16 / fp16), the exponent n added into the result's exponent field with one integer multiply-add.  The softmax warps are
+// bound by the XU pipe (MUFU.EX2: 4 lanes per clock per SM sub-partition, 64 exponentials per thread per key tile); sending
+// kPolyOf8 of every 8 score pairs through this form moves that share of the work to pipes that were half idle.
+__device__ __forceinline__ void exp2_poly_pair(float2 x, uint32_t& o0, uint32_t& o1) {
+  constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 xf = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 rn = __fadd2_rn(xf, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(rn, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(make_float2(0.05517027899622917f, 0.05517027899622917f), f, make_float2(0.2426076978445053f, 0.2426076978445053f));
+  p = __ffma2_rn(p, f, make_float2(0.693260908126831f, 0.693260908126831f));
+  p = __ffma2_rn(p, f, make_float2(0.9999282956123352f, 0.9999282956123352f));
+  o0 = __float_as_uint(p.x) + (__float_as_uint(xf.x) << 23);
+  o1 = __float_as_uint(p.y) + (__float_as_uint(xf.y) << 23);
+}
 
 template <typename T> struct AttnCfg {
   static constexpr int es = sizeof(T);
@@ -120,7 +138,7 @@ struct AttnItem {
   int b, h, t0, len, nkt;
 };
 
-template <typename T>
+template <typename T, int kPolyOf8>
 __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK,
                                                                       const __grid_constant__ CUtensorMap tmVT,
                                                                       const int64_t* __restrict__ lens, T* __restrict__ ctx,
@@ -220,7 +238,7 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: one flat sequence of key tiles
     if (lane == 0) {
-      const uint32_t fmt = kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16;
+      const uint32_t fmt = umma_fmt_of<T>();
       const uint32_t idesc_s = umma_idesc(fmt, kQ, kKV);
       const uint32_t idesc_o = umma_idesc(fmt, kQ, 64, v_mn ? 1u : 0u);
       const uint32_t q_addr = smem_u32(sQ);
@@ -355,8 +373,12 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 64; i += 2) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), k2, nm2);
-            sv[i] = __float_as_uint(fast_exp2(x.x));
-            sv[i + 1] = __float_as_uint(fast_exp2(x.y));
+            if (((i >> 1) & 7) < kPolyOf8) {           // compile-time split between the FMA-pipe form and MUFU.EX2
+              exp2_poly_pair(x, sv[i], sv[i + 1]);
+            } else {
+              sv[i] = __float_as_uint(fast_exp2(x.x));
+              sv[i + 1] = __float_as_uint(fast_exp2(x.y));
+            }
           }
         } else {
 #pragma unroll
@@ -398,8 +420,8 @@ __global__ void __launch_bounds__(kThreadsTc, 2) attention_tc_kernel(const __gri
           float a0[8], a1[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) { a0[i] = __uint_as_float(sv[cc + i]); a1[i] = __uint_as_float(sv[cc + 8 + i]); }
-          store8(reinterpret_cast<__nv_bfloat16*>(slice + ((ch0 ^ sw) * 16)), a0);
-          store8(reinterpret_cast<__nv_bfloat16*>(slice + (((ch0 + 1) ^ sw) * 16)), a1);
+          store8(reinterpret_cast<T*>(slice + ((ch0 ^ sw) * 16)), a0);
+          store8(reinterpret_cast<T*>(slice + (((ch0 + 1) ^ sw) * 16)), a1);
         } else {
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq)
@@ -485,9 +507,11 @@ int launch_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t 
     int rc = make_tmap(&tmVT, vt, C::es == 2 ? 1 : 0, 3, dims, strides, box);
     if (rc != 0) return rc;
   }
-  auto kern = attention_tc_kernel<T>;
-  static DeviceFlags attr_set;
-  SB_OPT_IN_SMEM(attr_set, kern, C::smem);
+  // ATTN_POLY (0..8, default 3): share (in eighths) of the exponentials computed on the FMA pipe, 16-bit operands only
+  const int poly = C::es == 2 ? tuning(TUNE_ATTN_POLY) : 0;
+  auto kern = poly == 0 ? attention_tc_kernel<T, 0> : (poly <= 2 ? attention_tc_kernel<T, 2> : (poly == 3 ? attention_tc_kernel<T, 3> : attention_tc_kernel<T, 4>));
+  static DeviceFlags attr_set[4];
+  SB_OPT_IN_SMEM(attr_set[poly == 0 ? 0 : (poly <= 2 ? 1 : (poly == 3 ? 2 : 3))], kern, C::smem);
   const int q_tiles = ceil_div(Tlen, kQ);
   const long long total = static_cast<long long>(B) * H * q_tiles;
   SB_REQUIRE(total < (1LL << 30), "attention_tc: too many work items");
@@ -522,14 +546,16 @@ int attention_simt(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int
 int attention_tc(const void* qk, int64_t qk_bs, int qk_ld, const void* vt, int64_t vt_bs, int vt_ld,
                  const int64_t* lens, void* ctx, int64_t ctx_bs, int ctx_ld, int B, int T, int H, int dtype,
                  cudaStream_t s) {
-  const int es = dtype == STYLER_BF16 ? 2 : 4;
-  SB_REQUIRE(vt != nullptr || dtype == STYLER_BF16,
-             "attention_tc: row-major V (vt == NULL) is only validated for bf16; pass V^T for fp32/tf32");
+  const int es = dtype != STYLER_F32 ? 2 : 4;
+  SB_REQUIRE(vt != nullptr || dtype != STYLER_F32,
+             "attention_tc: row-major V (vt == NULL) is only validated for 16-bit operands; pass V^T for fp32/tf32");
   SB_REQUIRE((static_cast<int64_t>(ctx_ld) * es) % 16 == 0 && (ctx_bs * es) % 16 == 0 &&
                  (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
              "attention_tc: ctx must be 16-byte aligned/strided");
   if (dtype == STYLER_BF16)
     return launch_tc<__nv_bfloat16>(qk, qk_bs, qk_ld, vt, vt_bs, vt_ld, lens, ctx, ctx_bs, ctx_ld, B, T, H, s);
+  if (dtype == STYLER_F16)
+    return launch_tc<__half>(qk, qk_bs, qk_ld, vt, vt_bs, vt_ld, lens, ctx, ctx_bs, ctx_ld, B, T, H, s);
   return launch_tc<float>(qk, qk_bs, qk_ld, vt, vt_bs, vt_ld, lens, ctx, ctx_bs, ctx_ld, B, T, H, s);
 }
 
@@ -539,10 +565,11 @@ extern "C" int styler_attention_fwd(const void* qk, int64_t qk_bstride, int32_t 
                                     int64_t vt_bstride, int32_t vt_ld, const int64_t* lens, void* ctx,
                                     int64_t ctx_bstride, int32_t ctx_ld, int32_t B, int32_t T, int32_t H,
                                     int32_t dtype, int32_t impl, void* stream) {
+  sb::TraceScope trace__("attention", stream, B, T, H, 0);
   using namespace sb;
   SB_REQUIRE(qk != nullptr && ctx != nullptr, "attention: null pointer");
   SB_REQUIRE(B > 0 && T > 0 && H > 0, "attention: bad shape B=%d T=%d H=%d", B, T, H);
-  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "attention: bad dtype %d", dtype);
+  SB_REQUIRE(sb::dtype_ok(dtype), "attention: bad dtype %d", dtype);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (impl == STYLER_IMPL_AUTO) impl = STYLER_IMPL_TC;
   if (impl == STYLER_IMPL_TC)

@@ -1,6 +1,7 @@
 // Shared helpers: status/error plumbing for the C ABI, dtype traits, small device utilities.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -15,6 +16,14 @@ namespace sb {
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+// Debug timeline (styler_debug_trace): when enabled, every leaf C-ABI entry records a CUDA event pair on its stream around
+// the kernels it enqueues -- also when it is called from inside a composite entry (decoder, FFT block, predictor, PostNet).
+struct TraceScope {
+  TraceScope(const char* name, void* stream, int a = 0, int b = 0, int c = 0, int d = 0);
+  ~TraceScope();
+  int idx;
+};
 
 // Per-DEVICE one-shot state.  A process may drive several GPUs from several threads (nn.DataParallel, train.py:33 of the
 // reference): function attributes such as the >48 KB dynamic-smem opt-in are per device, so "already done" flags are kept
@@ -32,7 +41,7 @@ int num_sms();   // SM count of the current device (cached per device)
 
 // A/B switches: read once from the environment (STYLER_<NAME>), overridable at run time through styler_set_tuning()
 // (tests and tools/prof_kernels.py flip them inside one process).
-enum Tuning { TUNE_TC_2CTA = 0, TUNE_TC_PERSIST, TUNE_CONV_WIN, TUNE_TC_BN, TUNE_TC_SMEM_KB, TUNE_PDL, TUNE_ATTN_PERSIST, TUNE_TC_WIDE, TUNE_COUNT };
+enum Tuning { TUNE_TC_2CTA = 0, TUNE_TC_PERSIST, TUNE_CONV_WIN, TUNE_TC_BN, TUNE_TC_SMEM_KB, TUNE_PDL, TUNE_ATTN_PERSIST, TUNE_TC_WIDE, TUNE_LSTM_MULTI, TUNE_ATTN_POLY, TUNE_LSTM_MMA, TUNE_COUNT };
 int tuning(Tuning t);
 
 #define SB_OPT_IN_SMEM(flags, kern, bytes)                                                                     \
@@ -84,6 +93,28 @@ template <> struct DT<__nv_bfloat16> {
   __device__ static __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+template <> struct DT<__half> {     // fp16 storage: 11 significand bits (tf32-class accuracy) at the bf16 tensor-pipe rate
+  static constexpr int code = STYLER_F16;
+  __device__ static __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  __device__ static __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+};
+inline bool dtype_ok(int dtype) { return dtype == STYLER_F32 || dtype == STYLER_BF16 || dtype == STYLER_F16; }
+// two floats -> one 32-bit word of two T elements (round to nearest even)
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// bf16 storage tolerates MUFU.TANH (2^-11); fp16 storage (tf32-class accuracy mode) uses ex2/rcp based forms (~1e-6 absolute)
+template <typename T> constexpr bool kBf16Math = DT<T>::code == STYLER_BF16;
+__device__ __forceinline__ float sigmoid_ex2(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_ex2(float x) { return fmaf(2.f, sigmoid_ex2(2.f * x), -1.f); }
+
 // 8 consecutive elements <-> 8 floats (16-byte access for bf16, 2x16 for fp32); pointers must be 16B aligned.
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -98,6 +129,15 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -107,6 +147,14 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
 
@@ -172,6 +220,7 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
   do {                                                           \
     if ((code) == STYLER_F32) { using T = float; __VA_ARGS__; }  \
     else if ((code) == STYLER_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((code) == STYLER_F16) { using T = __half; __VA_ARGS__; } \
     else { ::sb::set_error("unsupported dtype code %d", (int)(code)); return -1; } \
   } while (0)
 

@@ -11,7 +11,7 @@
 namespace sb {
 namespace {
 inline size_t align_up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
-inline size_t esz(int dtype) { return dtype == STYLER_BF16 ? 2 : 4; }
+inline size_t esz(int dtype) { return dtype != STYLER_F32 ? 2 : 4; }
 }  // namespace
 }  // namespace sb
 
@@ -26,7 +26,7 @@ extern "C" int styler_predictor_fwd(const styler_predictor_weights* w, const voi
                                     void* workspace, int64_t ws_bytes, void* stream) {
   SB_REQUIRE(w && x && out && workspace, "predictor: null pointer");
   SB_REQUIRE(B > 0 && T > 0 && w->channels > 0 && w->ks > 0, "predictor: bad shape");
-  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "predictor: bad dtype %d", dtype);
+  SB_REQUIRE(sb::dtype_ok(dtype), "predictor: bad dtype %d", dtype);
   const int C = w->channels;
   SB_REQUIRE(ws_bytes >= styler_predictor_workspace_bytes(B, T, C, dtype), "predictor: workspace too small");
   uint8_t* p = static_cast<uint8_t*>(workspace);
@@ -68,7 +68,7 @@ extern "C" int styler_postnet_fwd(const styler_postnet_weights* w, const void* m
                                   int64_t ws_bytes, void* stream) {
   SB_REQUIRE(w && mel_act && mel_f32 && post_out && workspace, "postnet: null pointer");
   SB_REQUIRE(w->n_layers >= 2 && w->n_layers <= 8 && w->channels > 0 && w->n_mel > 0 && w->ks > 0, "postnet: bad weights");
-  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "postnet: bad dtype %d", dtype);
+  SB_REQUIRE(sb::dtype_ok(dtype), "postnet: bad dtype %d", dtype);
   const int CH = w->channels, NM = w->n_mel, pad = (w->ks - 1) / 2;
   SB_REQUIRE(ws_bytes >= styler_postnet_workspace_bytes(B, T, CH, dtype), "postnet: workspace too small");
   uint8_t* p = static_cast<uint8_t*>(workspace);

@@ -215,12 +215,13 @@ int conv1d_simt(const styler_conv1d_args& a, cudaStream_t s) {
 }  // namespace sb
 
 extern "C" int styler_conv1d_fwd(const styler_conv1d_args* a, void* stream) {
+  sb::TraceScope trace__("conv1d", stream, a ? a->B : 0, a ? a->T : 0, a ? a->Cin : 0, a ? a->N * 100 + a->KS : 0);
   using namespace sb;
   SB_REQUIRE(a != nullptr && a->x != nullptr && a->w != nullptr, "conv1d: null x/w");
   SB_REQUIRE(a->B > 0 && a->T > 0 && a->Cin > 0 && a->N > 0 && a->KS > 0, "conv1d: bad shape B=%d T=%d Cin=%d N=%d KS=%d",
              a->B, a->T, a->Cin, a->N, a->KS);
   SB_REQUIRE(a->out != nullptr || a->out_f32 != nullptr || a->dot_out != nullptr || a->vt != nullptr, "conv1d: no output");
-  SB_REQUIRE(a->dtype == STYLER_F32 || a->dtype == STYLER_BF16, "conv1d: bad dtype %d", a->dtype);
+  SB_REQUIRE(sb::dtype_ok(a->dtype), "conv1d: bad dtype %d", a->dtype);
   SB_REQUIRE(a->dilation >= 0, "conv1d: bad dilation %d", a->dilation);
   SB_REQUIRE((a->act != STYLER_ACT_LRELU && a->act2 != STYLER_ACT_LRELU && a->residual_inv_lrelu == 0) ||
                  (a->act_slope > 0.f && a->act_slope < 1.f),

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       // WIDE tile (256 < BN <= 512, e.g. the 320-channel audio-encoder convs): one A stage feeds TWO MMAs of BN/2 columns each,
       // so the activations are pulled from L2 once per 128 x BN outputs (these convs are bound by operand bytes, not by the pipe)
       const int mma_n = BN > 256 ? BN / 2 : BN;
-      const uint32_t idesc = umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, CG2 ? 2 * kBM : kBM, mma_n);
+      const uint32_t idesc = umma_idesc(umma_fmt_of<T>(), CG2 ? 2 * kBM : kBM, mma_n);
       int g = 0, it = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
         const int ab = PERSIST ? (it & 1) : 0;
@@ -418,10 +418,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
       } else if constexpr (ACT == STYLER_ACT_TANH) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          if constexpr (sizeof(T) == 2) {              // bf16 storage: MUFU.TANH (rel. error 2^-11 < bf16 rounding)
+          if constexpr (kBf16Math<T>) {                // bf16 storage: MUFU.TANH (rel. error 2^-11 < bf16 rounding)
             float y;
             asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(v[i]));
             v[i] = y;
+          } else if constexpr (sizeof(T) == 2) {       // fp16 storage
+            v[i] = tanh_ex2(v[i]);
           } else {
             v[i] = tanhf(v[i]);
           }
@@ -649,9 +651,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_tc_kernel(const __grid_con
         if (dst2 != nullptr) dst2[i] = f;                      // e.g. rank 0's receive buffer over NVLink
         if (dsto != nullptr) {
           if constexpr (sizeof(T) == 2) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
             uint2 u;
-            u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+            u.x = pack2<T>(f.x, f.y); u.y = pack2<T>(f.z, f.w);
             reinterpret_cast<uint2*>(dsto)[i] = u;
           } else {
             reinterpret_cast<float4*>(dsto)[i] = f;
@@ -708,7 +709,7 @@ int cg2_mode() { return tuning(TUNE_TC_2CTA); }
 
 int pick_bn(const styler_conv1d_args& a, int m_tiles) {
   if (a.ln_gamma != nullptr || a.dot_w != nullptr) return (a.N <= 256 && a.N % 16 == 0) ? a.N : 0;
-  const int es0 = a.dtype == STYLER_BF16 ? 2 : 4;
+  const int es0 = a.dtype != STYLER_F32 ? 2 : 4;
   // full-width tile for 256 < N <= 512 that is not a multiple of 256 (the 320-channel convs): see the MMA issuer
   if (tuning(TUNE_TC_WIDE) != 0 && es0 == 2 && a.N > 256 && a.N <= 512 && a.N % 256 != 0 && a.N % 32 == 0 && (a.N * es0) % 128 == 0 &&
       a.out != nullptr && a.vt == nullptr && a.out_f32 == nullptr && m_tiles >= num_sms())
@@ -718,7 +719,7 @@ int pick_bn(const styler_conv1d_args& a, int m_tiles) {
     return forced;
   // Prefer tiles whose rows are whole 128-byte boxes (coalesced TMA epilogue); among those the largest tile that still
   // gives >= 2 waves of CTAs, otherwise the smallest tile >= 64 (more CTAs), otherwise the largest tile available.
-  const int es = a.dtype == STYLER_BF16 ? 2 : 4;
+  const int es = a.dtype != STYLER_F32 ? 2 : 4;
   for (int pass = 0; pass < 2; ++pass) {
     int largest = 0, smallest64 = 0;
     for (int bn = 256; bn >= 16; bn -= 16) {
@@ -890,7 +891,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace
 
 bool conv1d_tc_supported(const styler_conv1d_args& a, const char** why) {
-  const int es = a.dtype == STYLER_BF16 ? 2 : 4;
+  const int es = a.dtype != STYLER_F32 ? 2 : 4;
   auto fail = [&](const char* m) { if (why) *why = m; return false; };
   if (a.N % 16 != 0) return fail("N not a multiple of 16");
   if ((a.Cin * es) % 16 != 0) return fail("Cin row not a multiple of 16 bytes");
@@ -923,6 +924,7 @@ int conv1d_tc(const styler_conv1d_args& a, cudaStream_t s) {
   SB_REQUIRE(conv1d_tc_supported(a, &why), "conv1d_tc: unsupported arguments: %s", why ? why : "?");
   if (a.gn_partial == nullptr && conv1d_win_supported(a)) return conv1d_win(a, s);
   if (a.dtype == STYLER_BF16) return launch<__nv_bfloat16>(a, s);
+  if (a.dtype == STYLER_F16) return launch<__half>(a, s);
   return launch<float>(a, s);
 }
 

@@ -29,11 +29,11 @@ struct Ffn1Timing {
 
 extern "C" int64_t styler_fftblock_workspace_bytes(int32_t B, int32_t T, int32_t d_model, int32_t d_inner, int32_t dtype) {
   using namespace sb;
-  const size_t es = dtype == STYLER_BF16 ? 2 : 4;
+  const size_t es = dtype != STYLER_F32 ? 2 : 4;
   const size_t rows = static_cast<size_t>(B) * T;
   const size_t Tp = (static_cast<size_t>(T) + 7) / 8 * 8;
   size_t n = 0;
-  if (dtype == STYLER_BF16) n += align_up(rows * 3 * d_model * es);                                          // fused qkv
+  if (dtype != STYLER_F32) n += align_up(rows * 3 * d_model * es);                                          // fused qkv
   else n += align_up(rows * 2 * d_model * es) + align_up(static_cast<size_t>(B) * d_model * Tp * es);        // qk + V^T
   n += align_up(rows * d_model * es) * 2;                                                                      // ctx, y1
   n += align_up(rows * d_inner * es);                                                                          // FFN hidden
@@ -46,17 +46,17 @@ extern "C" int styler_fftblock_fwd(const styler_fft_weights* w, const void* x, i
   using namespace sb;
   SB_REQUIRE(w && x && y && workspace, "fftblock: null pointer");
   SB_REQUIRE(B > 0 && T > 0, "fftblock: bad shape B=%d T=%d", B, T);
-  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "fftblock: bad dtype %d", dtype);
+  SB_REQUIRE(sb::dtype_ok(dtype), "fftblock: bad dtype %d", dtype);
   const int D = w->d_model, DI = w->d_inner, H = w->n_head;
   SB_REQUIRE(D > 0 && DI > 0 && H > 0 && D == H * 64, "fftblock: d_model=%d must be n_head=%d x 64", D, H);
   SB_REQUIRE(ws_bytes >= styler_fftblock_workspace_bytes(B, T, D, DI, dtype), "fftblock: workspace too small (%lld bytes)",
              static_cast<long long>(ws_bytes));
-  const size_t es = dtype == STYLER_BF16 ? 2 : 4;
+  const size_t es = dtype != STYLER_F32 ? 2 : 4;
   const size_t rows = static_cast<size_t>(B) * T;
   const int Tp = (T + 7) / 8 * 8;
   uint8_t* p = static_cast<uint8_t*>(workspace);
   auto take = [&](size_t bytes) { uint8_t* r = p; p += align_up(bytes); return r; };
-  const bool v_rowmajor = dtype == STYLER_BF16;
+  const bool v_rowmajor = dtype != STYLER_F32;
   void* qkv = take(rows * (v_rowmajor ? 3 : 2) * D * es);
   void* vt = v_rowmajor ? nullptr : take(static_cast<size_t>(B) * D * Tp * es);
   void* ctx = take(rows * D * es);

@@ -508,6 +508,7 @@ using namespace sb;
 
 extern "C" int styler_embed_pos_fwd(const int64_t* src_seq, const float* emb, int32_t vocab, const float* pos, void* out,
                                     int32_t B, int32_t L, int32_t D, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("embed_pos", stream);
   SB_REQUIRE(src_seq && emb && pos && out, "embed_pos: null pointer");
   SB_REQUIRE(B > 0 && L > 0 && D % 8 == 0, "embed_pos: bad shape");
   const long long n = static_cast<long long>(B) * L * (D / 8);
@@ -521,6 +522,7 @@ extern "C" int styler_add_fwd(const void* a, int64_t a_bstride, int32_t a_ld, co
                               int32_t a2_ld, const void* rowvec, int32_t rowvec_ld, const float* pos, void* out,
                               int64_t o_bstride, int32_t o_ld, int32_t B, int32_t T, int32_t C, int32_t dtype,
                               void* stream) {
+  sb::TraceScope trace__("add", stream);
   SB_REQUIRE(out, "add: null pointer");
   SB_REQUIRE(B > 0 && T > 0 && C % 8 == 0 && a_ld % 8 == 0 && o_ld % 8 == 0 && a_bstride % 8 == 0 && o_bstride % 8 == 0 &&
                  (a2 == nullptr || (a2_ld % 8 == 0 && a2_bstride % 8 == 0)) && (rowvec == nullptr || rowvec_ld % 8 == 0),
@@ -537,6 +539,7 @@ extern "C" int styler_add_fwd(const void* a, int64_t a_bstride, int32_t a_ld, co
 }
 
 extern "C" int styler_cast_fwd(const float* x, void* out, int64_t n, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("cast", stream);
   SB_REQUIRE(x && out && n > 0, "cast: bad arguments");
   SB_DISPATCH_DTYPE(dtype, T, (cast_kernel<T><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                                   x, static_cast<T*>(out), n)));
@@ -546,6 +549,7 @@ extern "C" int styler_cast_fwd(const float* x, void* out, int64_t n, int32_t dty
 
 extern "C" int styler_lrelu_mean_fwd(const void* a, const void* b, const void* c, float slope_in, float slope_out, void* out,
                                      int64_t n, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("lrelu_mean", stream);
   SB_REQUIRE(a && out && n > 0 && n % 8 == 0, "lrelu_mean: bad arguments (n must be a multiple of 8)");
   SB_REQUIRE(slope_in > 0.f && slope_in <= 1.f && slope_out >= 0.f && slope_out <= 1.f, "lrelu_mean: bad slopes");
   SB_REQUIRE(b != nullptr || c == nullptr, "lrelu_mean: pass inputs in order (a, b, c)");
@@ -566,6 +570,7 @@ extern "C" int styler_f0_norm_fwd(const float* f0, const int64_t* lens, float* o
 }
 
 extern "C" int styler_quantize_index_fwd(const float* x, int32_t* idx, int64_t n, void* stream) {
+  sb::TraceScope trace__("quantize_index", stream);
   SB_REQUIRE(x && idx && n > 0, "quantize_index: bad arguments");
   quantize_index_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, idx, n);
   SB_LAUNCH_OK();
@@ -574,6 +579,7 @@ extern "C" int styler_quantize_index_fwd(const float* x, int32_t* idx, int64_t n
 
 extern "C" int styler_onehot_conv_fwd(const int32_t* idx, const float* wg, const float* bias, void* out, int32_t B,
                                       int32_t T, int32_t C, int32_t nidx, int32_t KS, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("onehot_conv", stream);
   SB_REQUIRE(idx && wg && bias && out, "onehot_conv: null pointer");
   SB_REQUIRE(B > 0 && T > 0 && C % 8 == 0 && nidx > 0 && KS > 0, "onehot_conv: bad shape");
   const long long n = static_cast<long long>(B) * T * (C / 8);
@@ -586,6 +592,7 @@ extern "C" int styler_onehot_conv_fwd(const int32_t* idx, const float* wg, const
 extern "C" int styler_groupnorm_relu_fwd(void* x, int64_t bstride, int32_t ld, const float* gamma, const float* beta,
                                          float* stats_ws, int32_t B, int32_t T, int32_t C, int32_t ch_per_group, float eps,
                                          int32_t dtype, void* stream) {
+  sb::TraceScope trace__("groupnorm_relu", stream);
   SB_REQUIRE(x && gamma && beta && stats_ws, "groupnorm: null pointer");
   SB_REQUIRE(B > 0 && T > 0 && ch_per_group % 8 == 0 && C % ch_per_group == 0 && ld % 8 == 0 && bstride % 8 == 0 && al16(x),
              "groupnorm: bad shape/alignment");
@@ -604,6 +611,7 @@ extern "C" int styler_groupnorm_relu_fwd(void* x, int64_t bstride, int32_t ld, c
 extern "C" int styler_groupnorm_relu_partial_fwd(void* x, int64_t bstride, int32_t ld, const float* gamma, const float* beta,
                                                  const float* partial, int32_t n_part, float* stats_ws, int32_t B, int32_t T,
                                                  int32_t C, float eps, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("groupnorm_relu_partial", stream);
   SB_REQUIRE(x && gamma && beta && partial && stats_ws, "groupnorm_partial: null pointer");
   SB_REQUIRE(B > 0 && T > 0 && C % 16 == 0 && ld % 8 == 0 && bstride % 8 == 0 && al16(x) && n_part == (T + 127) / 128,
              "groupnorm_partial: bad shape/alignment (n_part must be ceil(T/128))");
@@ -621,6 +629,7 @@ extern "C" int styler_groupnorm_relu_partial_fwd(void* x, int64_t bstride, int32
 extern "C" int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const int64_t* mel_len,
                                          const int64_t* src_len, void* out, int64_t o_bstride, int32_t o_ld, int32_t B,
                                          int32_t Tr, int32_t L, int32_t C, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("mel_calibrator", stream);
   SB_REQUIRE(x && mel_len && src_len && out, "mel_calibrator: null pointer");
   SB_REQUIRE(B > 0 && Tr > 0 && L > 0 && C % 8 == 0 && x_ld % 8 == 0 && o_ld % 8 == 0 && x_bstride % 8 == 0 &&
                  o_bstride % 8 == 0 && al16(x) && al16(out), "mel_calibrator: bad shape/alignment");
@@ -634,6 +643,7 @@ extern "C" int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32
 
 extern "C" int styler_classifier_tail_fwd(const void* h, int64_t h_bstride, int32_t h_ld, const float* w, const float* b,
                                           float* out, int32_t B, int32_t L, int32_t C, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("classifier_tail", stream);
   SB_REQUIRE(h && w && b && out && B > 0 && L > 0 && C > 0, "classifier_tail: bad arguments");
   SB_REQUIRE(C != 256 || (al16(h) && h_ld % 8 == 0 && h_bstride % 8 == 0 && al16(w)), "classifier_tail: rows must be 16-byte aligned");
   SB_DISPATCH_DTYPE(dtype, TT, (classifier_tail_kernel<TT><<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -644,6 +654,7 @@ extern "C" int styler_classifier_tail_fwd(const void* h, int64_t h_bstride, int3
 
 extern "C" int styler_duration_round_fwd(const float* log_d, float* dur, int64_t n, float log_offset, float d_control,
                                          void* stream) {
+  sb::TraceScope trace__("duration_round", stream);
   SB_REQUIRE(log_d && dur && n > 0, "duration_round: bad arguments");
   duration_round_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(log_d, dur, n, log_offset,
                                                                                            d_control);
@@ -655,10 +666,11 @@ extern "C" int styler_length_regulator_fwd(const void* x, int64_t x_bstride, int
                                            const float* dur_f32, void* out, int64_t o_bstride, int32_t o_ld,
                                            int64_t* mel_len, int32_t* cum_ws, int32_t B, int32_t L, int32_t Tmax, int32_t C,
                                            int32_t dtype, void* stream) {
+  sb::TraceScope trace__("length_regulator", stream);
   SB_REQUIRE(x && out && mel_len && cum_ws, "length_regulator: null pointer");
   SB_REQUIRE((dur_i64 != nullptr) != (dur_f32 != nullptr), "length_regulator: exactly one of dur_i64 / dur_f32");
-  SB_REQUIRE(dtype == STYLER_F32 || dtype == STYLER_BF16, "length_regulator: bad dtype");
-  const int es = dtype == STYLER_BF16 ? 2 : 4;
+  SB_REQUIRE(sb::dtype_ok(dtype), "length_regulator: bad dtype");
+  const int es = dtype != STYLER_F32 ? 2 : 4;
   SB_REQUIRE(B > 0 && L > 0 && L <= 8192 && Tmax >= 0 && C > 0, "length_regulator: bad shape");
   SB_REQUIRE((C * es) % 16 == 0 && (static_cast<int64_t>(x_ld) * es) % 16 == 0 && (static_cast<int64_t>(o_ld) * es) % 16 == 0 &&
                  (x_bstride * es) % 16 == 0 && (o_bstride * es) % 16 == 0 && al16(x) && al16(out),
@@ -684,6 +696,7 @@ extern "C" int styler_bucket_embed_sum_fwd(const void* text, const void* spk, co
                                            int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx,
                                            float* p_scaled, float* e_scaled, void* pitch_emb_out, void* energy_emb_out,
                                            int32_t B, int32_t T, int32_t C, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("bucket_embed_sum", stream);
   SB_REQUIRE(p_val && e_val && pitch_bins && energy_bins && pitch_emb && energy_emb, "bucket_embed_sum: null pointer");
   SB_REQUIRE(out == nullptr || (text != nullptr && spk != nullptr), "bucket_embed_sum: out needs text and spk");
   SB_REQUIRE(out != nullptr || out_noisy == nullptr, "bucket_embed_sum: out_noisy needs out");

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace sb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -182,6 +184,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 enum : uint32_t { UMMA_FMT_F16 = 0, UMMA_FMT_BF16 = 1, UMMA_FMT_TF32 = 2 };
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+template <typename T> __host__ __device__ constexpr uint32_t umma_fmt_of() {   // operand format of storage type T
+  return sizeof(T) == 4 ? UMMA_FMT_TF32 : (DT<T>::code == STYLER_F16 ? UMMA_FMT_F16 : UMMA_FMT_BF16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.

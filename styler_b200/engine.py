@@ -5,6 +5,8 @@
 then runs the eval-mode forward of styler.py:39-58 / modules.py:311-387 as a sequence of kernel launches on the current
 CUDA stream.  Precision modes:
   "bf16": bf16 activations/weights, tcgen05 kind::f16, fp32 accumulate / LayerNorm / softmax / LSTM state (throughput mode)
+  "fp16": IEEE-half activations/weights, tcgen05 kind::f16 with f16 operands: the bf16 kernels and speed with an 11-bit
+          significand (tf32-class accuracy: meets the 1e-3 fp32-parity tolerance on the mels); accurate ex2/rcp tanh / sigmoid
   "tf32": fp32 activations/weights, tcgen05 kind::tf32 (fp32-parity mode on tensor cores)
   "fp32": fp32 activations/weights, CUDA-core fp32 kernels only (exact-fp32 parity mode, slow)
 """
@@ -62,20 +64,20 @@ class _NS(dict):
 
 class Engine:
     def __init__(self, state_dict, device, precision="bf16"):
-        if precision not in ("bf16", "tf32", "fp32"):
-            raise ValueError("precision must be bf16 | tf32 | fp32")
+        if precision not in ("bf16", "fp16", "tf32", "fp32"):
+            raise ValueError("precision must be bf16 | fp16 | tf32 | fp32")
         self.precision = precision
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("styler_b200.Engine needs a CUDA device: the product path has no CPU implementation")
-        self.dt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision, torch.float32)
         self.impl = IMPL_SIMT if precision == "fp32" else IMPL_AUTO
         self.attn_impl = IMPL_SIMT if precision == "fp32" else IMPL_TC
         self._pos_cache = {}
         self.inter = {}
         self.last_packed = None
         self.result_mirror = None            # uint8 tensor of packed_nbytes(B, T) in PEER memory: forward() also writes its results there
-        self.v_rowmajor = precision == "bf16"   # attention reads V row-major from the fused QKV buffer (MN-major B operand;
+        self.v_rowmajor = precision in ("bf16", "fp16")   # attention reads V row-major from the fused QKV buffer (MN-major B operand;
                                                # validated for kind::f16 only -- the fp32 modes keep the transposed-V layout)
         import os
         self.use_streams = os.environ.get("STYLER_NO_STREAMS", "0") != "1"   # four audio-encoder branches on side streams
@@ -249,31 +251,40 @@ class Engine:
             c = ops.bilstm_layer(gx, whh, self.dt)
         return c
 
-    def audio_encoder(self, mel_target, p_idx, e_idx, mel_aug, mel_len, src_len, L, join=True, classify=False):
+    def audio_encoder(self, mel_target, p_idx, e_idx, mel_aug, mel_len, src_len, L, join=True, classify=False, tails=None):
         """modules.py:164-201 on the padded grid: conv stacks + GroupNorm + ReLU @Tr, Mel Calibrator, 2-layer BiLSTMs @L.
         The four style-factor branches are independent: each runs on its own CUDA stream so the latency-bound BiLSTM
         recurrences overlap the other branches' convolutions instead of serialising.
         classify: also run the three augmentation classifiers (modules.py:319-321) at the tail of their branch's stream.  Their
         posteriors are forward OUTPUTS that nothing downstream consumes, so the main stream only waits for the branch encodings
-        (`join_branches`, per-branch events) and picks the posteriors up at the very end of the forward (`join_audio_streams`)."""
+        (`join_branches`, per-branch events) and picks the posteriors up at the very end of the forward (`join_audio_streams`).
+        tails: optional per-branch callables c -> tensor(s), run on the branch's stream right behind its encoding (the per-factor
+        up-projection MLPs of modules.py:334-347: four independent chains instead of eight serial launches on the main stream);
+        their results are returned as a second list and are covered by the branch events."""
         ins = (mel_target, p_idx, e_idx, mel_aug)
         names = ("d", "p", "e", None)
         self._post = [None, None, None]
         if not self.use_streams:
             outs = [self._audio_branch(br, xin, mel_len, src_len, L) for br, xin in zip(self.w.branches, ins)]
+            ups = [t(c) for t, c in zip(tails, outs)] if tails is not None else None
             if classify:
                 self._post = [self._classifier(outs[i], self.w.cls[names[i]]) for i in range(3)]
-            return outs
+            return outs if tails is None else (outs, ups)
         main = torch.cuda.current_stream(self.device)
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
         start = torch.cuda.Event()
         start.record(main)
-        outs, self._branch_events = [], []
+        outs, ups, self._branch_events = [], [], []
         for i, (st, br, xin) in enumerate(zip(self._streams, self.w.branches, ins)):
             st.wait_event(start)
             with torch.cuda.stream(st):
                 c = self._audio_branch(br, xin, mel_len, src_len, L)
+                if tails is not None:
+                    up = tails[i](c)
+                    for t_ in (up if isinstance(up, (tuple, list)) else (up,)):
+                        t_.record_stream(main)
+                    ups.append(up)
                 ev = torch.cuda.Event()
                 ev.record(st)
                 if classify and names[i] is not None:
@@ -284,7 +295,7 @@ class Engine:
             self._branch_events.append(ev)
         if join:
             self.join_audio_streams()
-        return outs
+        return outs if tails is None else (outs, ups)
 
     def join_branches(self):
         """Main stream waits for the four branch ENCODINGS only (not for the classifiers queued behind them)."""
@@ -339,21 +350,23 @@ class Engine:
         # the audio-encoder branches (side streams) overlap the text encoder and speaker projections (this stream)
         p_idx, e_idx = ops.quantize_index(p_norm), ops.quantize_index(e_input)                          # utils.py:417-429
         mel_t, mel_a = self._act(mel_target), self._act(mel_aug)
-        d_enc, p_enc, e_enc, n_enc = self.audio_encoder(mel_t, p_idx, e_idx, mel_a, mel_len, src_len, L, join=False, classify=True)
+        spk_in = self._act(speaker_embed).unsqueeze(0)                                                  # [1,B,512]
+
+        def pitch_tail(p_enc):                         # modules.py:332,338-340 on the pitch branch's own stream
+            spk_p = ops.conv1d(spk_in, w.slp[0], w.slp[1], act=ACT_RELU, impl=self.impl)[0]             # [B,128]
+            return self._mlp2(ops.add(p_enc, rowvec=spk_p), w.mlp["pitch"]), spk_p
+
+        tails = (lambda c: self._mlp2(c, w.mlp["duration"]), pitch_tail, lambda c: self._mlp2(c, w.mlp["energy"]),
+                 lambda c: self._mlp2(c, w.mlp["residual"], out=enc[..., 1024:1280]))
+        (d_enc, p_enc, e_enc, n_enc), (d_up, (p_up, spk_p), e_up, n_up) = self.audio_encoder(
+            mel_t, p_idx, e_idx, mel_a, mel_len, src_len, L, join=False, classify=True, tails=tails)
         text = self.text_encoder(src_seq, src_len, out=enc[..., 0:256])
         neck = ops.conv1d(text, w.tld[0], w.tld[1], act=ACT_RELU, impl=self.impl)                      # [B,L,4]
-        spk_in = self._act(speaker_embed).unsqueeze(0)                                                  # [1,B,512]
-        spk_p = ops.conv1d(spk_in, w.slp[0], w.slp[1], act=ACT_RELU, impl=self.impl)[0]                 # [B,128]
         spk = ops.conv1d(spk_in, w.sl[0], w.sl[1], act=ACT_RELU, impl=self.impl)[0]                     # [B,256]
         neck_up = ops.conv1d(neck, w.tlu[0], w.tlu[1], act=ACT_RELU, impl=self.impl)                    # [B,L,256]
         ops.add(None, rowvec=spk, out=enc[..., 512:768])
         self.join_branches()
         post = tuple(self._post)                       # produced on the side streams; valid after join_audio_streams() (end of forward)
-        p_enc_sp = ops.add(p_enc, rowvec=spk_p)                                                         # modules.py:332
-        d_up = self._mlp2(d_enc, w.mlp["duration"])
-        p_up = self._mlp2(p_enc_sp, w.mlp["pitch"])
-        e_up = self._mlp2(e_enc, w.mlp["energy"])
-        n_up = self._mlp2(n_enc, w.mlp["residual"], out=enc[..., 1024:1280])
         ops.add(neck_up, p_up, out=enc[..., 256:512])                                                   # modules.py:350
         ops.add(neck_up, e_up, out=enc[..., 768:1024])
         dur_in = ops.add(neck_up, d_up)
@@ -394,6 +407,18 @@ class Engine:
                 e_target=None, max_src_len=None, max_mel_len=None, speaker_embed=None, d_control=1.0, p_control=1.0,
                 e_control=1.0):
         """styler.py:39-58.  Returns the reference's 9-tuple (mels/predictions fp32, masks bool, lengths int64)."""
+        ctx = self.forward_front(src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target, p_target, e_target,
+                                 max_src_len, max_mel_len, speaker_embed, d_control, p_control, e_control, join=False)
+        return self.forward_back(ctx)
+
+    def forward_front(self, src_seq, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, d_target=None, p_target=None,
+                      e_target=None, max_src_len=None, max_mel_len=None, speaker_embed=None, d_control=1.0, p_control=1.0,
+                      e_control=1.0, join=True):
+        """First stage of the forward: style encoders + variance adaptor (styler.py:41-49) up to the decoder input.  Returns a
+        context for `forward_back`.  The two stages are separate so that a serving loop can run stage one of batch i+1 under
+        stage two of batch i (model.PipelinedSTYLER): stage one is latency-bound (BiLSTM recurrences, many small kernels) and
+        leaves most SMs idle, stage two is four fifths of the FLOPs.
+        join: wait here for the side streams (the DAT posteriors are then complete when this stage is)."""
         dev = self.device
         src_seq = src_seq.to(dev).contiguous()
         src_len = src_len.to(dev, torch.int64).contiguous()
@@ -416,6 +441,17 @@ class Engine:
             T = int(max_mel_len) if max_mel_len else int(tot.max().item())     # the one host sync of the path
             x, x_noisy, _, p_pred, e_pred, out_len = self.variance_adapt(enc, log_d, T, None, None, p_target, e_target,
                                                                          d_control, p_control, e_control, duration=duration)
+        if join:
+            self.join_audio_streams()
+        ctx = _NS(xx=self._xx, out_len=out_len, B=B, L=L, T=T, src_len=src_len, log_d=log_d, p_pred=p_pred, e_pred=e_pred,
+                  post=post, joined=join)
+        self._xx = None
+        return ctx
+
+    def forward_back(self, ctx):
+        """Second stage: clean + noisy decode, mel_linear, PostNet (styler.py:52-57) and the packed result buffer."""
+        dev = self.device
+        B, L, T, out_len = ctx.B, ctx.L, ctx.T, ctx.out_len
         # styler.py:52,55: clean decode and noisy decode (x.detach() + noise_encoding) -- batched as one [2B] pass.
         # The four mel tensors and the lengths land in ONE contiguous buffer [mel | mel_noisy | postnet | postnet_noisy | len]
         # so that the data-parallel gather to rank 0 (dist.AsyncGather.launch_packed) is a single NCCL operation.
@@ -425,16 +461,17 @@ class Engine:
             if packed is None or self.result_mirror.numel() != packed_nbytes(B, T):
                 raise ValueError("result_mirror must hold exactly %d bytes for B=%d, T=%d (and needs the PostNet)" % (packed_nbytes(B, T), B, T))
             mirror, mel_m, post_m = packed_views(B, T, dev, self.result_mirror)
-        mel2, post2 = self.decode(self._xx, out_len.repeat(2), mel_out, post_out, mel_m, post_m)
-        self.join_audio_streams()                      # the DAT posteriors (side streams) are outputs of this forward
+        mel2, post2 = self.decode(ctx.xx, out_len.repeat(2), mel_out, post_out, mel_m, post_m)
+        post = ctx.post
+        if not ctx.joined:
+            self.join_audio_streams()                  # the DAT posteriors (side streams) are outputs of this forward
         if mirror is not None:
             mirror[1].copy_(out_len)
         if packed is not None:
             packed[1].copy_(out_len)
         self.last_packed = packed[0] if packed is not None else None
-        self._xx = None
         mel, mel_n, post_mel, post_mel_n = mel2[:B], mel2[B:], post2[:B], post2[B:]
         ar = torch.arange(L, device=dev)
-        src_mask = ar.unsqueeze(0) >= src_len.unsqueeze(1)
+        src_mask = ar.unsqueeze(0) >= ctx.src_len.unsqueeze(1)
         mel_mask = torch.arange(T, device=dev).unsqueeze(0) >= out_len.unsqueeze(1)
-        return (mel, mel_n), (post_mel, post_mel_n), log_d, p_pred, e_pred, src_mask, mel_mask, out_len, post
+        return (mel, mel_n), (post_mel, post_mel_n), ctx.log_d, ctx.p_pred, ctx.e_pred, src_mask, mel_mask, out_len, post

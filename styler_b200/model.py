@@ -462,3 +462,145 @@ class GraphedSTYLER:
     def __call__(self, *args, **kwargs):
         self.load_inputs(*args, **kwargs)
         return self.replay()
+
+
+class PipelinedSTYLER:
+    """Two-stage software pipeline over consecutive batches of one geometry (a serving loop's view of the forward).
+
+    Stage one of a forward (style encoders + variance adaptor, styler.py:41-49) is latency-bound: BiLSTM recurrences, ~90 small
+    kernels, most SMs idle for about a quarter of the step.  Stage two (decoder, mel_linear, PostNet, styler.py:52-57) is four
+    fifths of the FLOPs in a handful of machine-filling kernels.  Here each stage is its own CUDA graph per slot: stage one runs
+    on a LOW-priority stream, stage two on a HIGH-priority stream, and `submit` of batch i+1 enqueues its stage one while stage
+    two of batch i is still running -- the block scheduler hands SM slots to the decoder's CTAs first and fills what they leave
+    (kernel tails, the gaps between launches) with the next batch's encoder work.  Results are bitwise those of `STYLER.forward`.
+
+        pipe = PipelinedSTYLER(model, args, kwargs)          # capture (fixed geometry, as GraphedSTYLER)
+        k = pipe.submit(*args, **kwargs)                     # enqueue one batch; returns its slot
+        out = pipe.outputs(k); pipe.done(k).synchronize()    # the 9-tuple of styler.py:58 (static buffers of slot k)
+    A slot's outputs are overwritten by the submit `slots` batches later; that submit waits (stream order) for the events
+    passed as `after=` -- record one behind whatever still reads the slot (D2H copy, gather).
+    """
+
+    def __init__(self, model, example_args, example_kwargs, slots=2, result_mirrors=None, back_priority=-1):
+        self.model = model
+        eng = model._engine_for()
+        self._eng = eng
+        dev = eng.device
+        if example_kwargs.get("d_target") is None and not example_kwargs.get("max_mel_len"):
+            raise ValueError("PipelinedSTYLER needs d_target or max_mel_len (no host sync may happen inside a CUDA graph)")
+        self.slots = int(slots)
+        self.s_front = torch.cuda.Stream(device=dev, priority=0)
+        self.s_back = torch.cuda.Stream(device=dev, priority=back_priority)
+        self.static_args, self.static_kwargs, self.g_front, self.g_back, self.ctx, self.out, self.packed = [], [], [], [], [], [], []
+        self.ev_front = [None] * self.slots
+        self.ev_back = [None] * self.slots
+        self._n = 0
+        with torch.cuda.device(dev):
+            for k in range(self.slots):
+                sa = [a.to(dev).clone() if torch.is_tensor(a) else a for a in example_args]
+                skw = {n: (v.to(dev).clone() if torch.is_tensor(v) else v) for n, v in example_kwargs.items()}
+                T = skw.get("max_mel_len") or int(skw["d_target"].sum(1).max().item())
+                skw["max_mel_len"] = T
+                eng._pos("dec", T)
+                eng._pos("enc", sa[0].shape[1])
+                if k == 0:                                   # eager warm-up on the capture streams: allocator pools, side streams
+                    self.s_front.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(self.s_front):
+                        model(*sa, **skw)
+                    torch.cuda.synchronize(dev)
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, stream=self.s_front):
+                    ctx = eng.forward_front(*sa, **skw, join=True)
+                eng.result_mirror = result_mirrors[k] if result_mirrors is not None else None
+                try:
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2, stream=self.s_back):
+                        out = eng.forward_back(ctx)
+                finally:
+                    eng.result_mirror = None
+                self.static_args.append(sa)
+                self.static_kwargs.append(skw)
+                self.g_front.append(g1)
+                self.g_back.append(g2)
+                self.ctx.append(ctx)
+                self.out.append(out)
+                self.packed.append(eng.last_packed)
+            torch.cuda.synchronize(dev)
+
+    def _check(self, k, kwargs):
+        if self.model._engine is not self._eng:
+            raise RuntimeError("PipelinedSTYLER: the model was moved / reloaded / re-precisioned after capture; build a new one")
+        for n, v in kwargs.items():
+            sk = self.static_kwargs[k]
+            if not torch.is_tensor(v) and n in sk and sk[n] != v and not (n == "max_mel_len" and v is None):
+                raise ValueError("PipelinedSTYLER: %s=%r differs from the captured %r" % (n, v, sk[n]))
+
+    def load_inputs(self, k, *args, **kwargs):
+        """Copy a batch (device or pinned-host tensors) into slot k's static inputs on the CURRENT stream, after the stage-one
+        graph that last read them."""
+        self._check(k, kwargs)
+        cur = torch.cuda.current_stream(self._eng.device)
+        if self.ev_front[k] is not None:
+            cur.wait_event(self.ev_front[k])
+        for dst, src in zip(self.static_args[k], args):
+            if torch.is_tensor(dst):
+                dst.copy_(src, non_blocking=True)
+        for n, v in kwargs.items():
+            dst = self.static_kwargs[k].get(n)
+            if torch.is_tensor(dst):
+                dst.copy_(v, non_blocking=True)
+
+    def next_slot(self):
+        return self._n % self.slots
+
+    def run(self, k=None, after=(), pre_back=None, post_back=None):
+        """Enqueue both stages of slot k over whatever its static inputs hold (loaded on the current stream).
+        after: events the stage-two graph must wait for before it overwrites slot k's results.
+        pre_back / post_back: callables run with the stage-two stream current, right before / after its graph launch
+        (gather flow control, dist.AsyncPeerGather.begin / launch_packed)."""
+        dev = self._eng.device
+        if k is None:
+            k = self.next_slot()
+        self._n += 1
+        cur = torch.cuda.current_stream(dev)
+        ev_in = torch.cuda.Event()
+        ev_in.record(cur)
+        self.s_front.wait_event(ev_in)
+        if self.ev_back[k] is not None:
+            self.s_front.wait_event(self.ev_back[k])         # stage two of the batch that last used this slot has read its input
+        with torch.cuda.stream(self.s_front):
+            self.g_front[k].replay()
+            ev = torch.cuda.Event()
+            ev.record(self.s_front)
+        self.ev_front[k] = ev
+        self.s_back.wait_event(ev)
+        for e in after:
+            if e is not None:
+                self.s_back.wait_event(e)
+        with torch.cuda.stream(self.s_back):
+            if pre_back is not None:
+                pre_back()
+            self.g_back[k].replay()
+            ev2 = torch.cuda.Event()
+            ev2.record(self.s_back)
+            self.ev_back[k] = ev2
+            if post_back is not None:
+                post_back()
+        return k
+
+    def submit(self, *args, after=(), **kwargs):
+        k = self.next_slot()
+        self.load_inputs(k, *args, **kwargs)
+        return self.run(k, after=after)
+
+    def outputs(self, k):
+        return self.out[k]
+
+    def done(self, k):
+        return self.ev_back[k]
+
+    def join(self):
+        """Make the current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self._eng.device)
+        cur.wait_stream(self.s_front)
+        cur.wait_stream(self.s_back)

@@ -4,6 +4,7 @@ oracle/make_golden.py from the unmodified reference) and against the CPU oracle 
 Tolerances (tensor-normalised max error, |got-ref|.max() / |ref|.max(); north_star: 1e-3 relative on fp32 mels):
   fp32 mode (CUDA cores)      : 1e-4 everywhere
   tf32 mode (tcgen05 tf32)    : 1e-3 on the four mels, 5e-3 on predictor outputs
+  fp16 mode (tcgen05 f16)     : the SAME gates as tf32 (11-bit significand, fp16 storage; runs at the bf16 speed)
   bf16 mode (tcgen05 bf16)    : 1e-2 on the mels, 3e-2 on predictor outputs (bf16 has an 8-bit mantissa; SURVEY.md section 7);
                                 2e-2 on the stored inspection encodings (kept in bf16 storage, i.e. rounded once more)
 Integer outputs (mel_len, masks) are bit exact in every mode.
@@ -20,6 +21,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 TOL = {"fp32": dict(mel=1e-4, pred=1e-4, post=1e-4, enc=1e-4), "tf32": dict(mel=1e-3, pred=5e-3, post=2e-3, enc=1e-3),
+       "fp16": dict(mel=1e-3, pred=5e-3, post=2e-3, enc=2.5e-3),   # enc: inspection tensors are kept in fp16 STORAGE (one more rounding)
        "bf16": dict(mel=1e-2, pred=3e-2, post=3e-2, enc=2e-2)}   # enc: inspection tensors, which live in bf16 STORAGE in bf16 mode
 
 
@@ -46,7 +48,7 @@ def run(model, batch, cuda):
     return mg.flatten_outputs(out)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp16", "bf16"])
 @pytest.mark.parametrize("case", sorted(mg.CASES))
 def test_forward_vs_reference_golden(cuda, case, precision):
     gold = torch.load(os.path.join(GOLD, case + ".pt"))
@@ -73,7 +75,7 @@ def test_forward_vs_reference_golden(cuda, case, precision):
     print("\n%s/%s " % (case, precision) + " ".join("%s=%.1e" % kv for kv in errs.items()))
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "fp16", "bf16"])
 def test_forward_config3_shape_vs_oracle(cuda, precision):
     """BASELINE config 3 geometry (L=128 -> T=1024, teacher-forced 8 frames/phoneme) at B=4 against the CPU oracle,
     plus size-independent properties: padded mel frames equal mel_linear.bias (SURVEY 8(a) trap 2), FFT-block outputs
@@ -119,7 +121,7 @@ def test_forward_bench_shape_b64_vs_oracle(cuda):
     with torch.no_grad():
         ref = mg.flatten_outputs(so.styler_forward(sd, *args, **kw))
     assert ref["mel"].shape == (3, 1024, 80)
-    for precision in ("bf16", "tf32"):
+    for precision in ("bf16", "fp16", "tf32"):
         model = STYLER(precision=precision)
         model.load_state_dict(sd)
         model = model.to(cuda).eval()
@@ -177,7 +179,7 @@ def test_fftblock_config2_geometry(cuda):
     p = "decoder.layer_stack.2."
     with torch.no_grad():
         ref = so.fft_block(sd, p, x, mask)
-    for precision, tol in (("fp32", 2e-5), ("tf32", 1e-3), ("bf16", 2e-2)):
+    for precision, tol in (("fp32", 2e-5), ("tf32", 1e-3), ("fp16", 1e-3), ("bf16", 2e-2)):
         eng = Engine(sd, cuda, precision)
         got = eng.fft_block(x.to(cuda, eng.dt), lens.to(cuda), eng.w.dec_layers[2])
         torch.cuda.synchronize()
@@ -285,3 +287,37 @@ def test_cuda_graph_replay_matches_eager(cuda):
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / n * 1e3
     print("\nB=2 L=40 T=%d forward: eager %.2f ms, CUDA-graph replay %.2f ms" % (T, timeit(lambda: model(*a2, **k2)), timeit(lambda: g(*a2, **k2))))
+
+
+def test_pipelined_batches_match_eager(cuda):
+    """PipelinedSTYLER: stage one (encoders + variance adaptor) of batch i+1 runs on a low-priority stream under stage two
+    (decoder + PostNet) of batch i; every batch's results are bitwise those of the plain forward."""
+    from styler_b200 import STYLER, PipelinedSTYLER
+    sd = so.make_state_dict(0)
+    model = STYLER(precision="bf16")
+    model.load_state_dict(sd)
+    model = model.to(cuda).eval()
+    batches = [so.make_inputs(B=3, L=48, seed=60 + i, d_mode="const", frames=6) for i in range(5)]
+    to = lambda a, k: ([x.to(cuda) for x in a], {n: (v.to(cuda) if torch.is_tensor(v) else v) for n, v in k.items()})
+    calls = [to(*mg.call_kwargs(dict(b, max_mel_len=48 * 6))) for b in batches]
+    eager = []
+    for a, k in calls:
+        o = mg.flatten_outputs(model(*a, **k))
+        eager.append({n: v.clone() for n, v in o.items()})
+    pipe = PipelinedSTYLER(model, *calls[0])
+    keys = ("mel", "mel_noisy", "mel_postnet", "mel_postnet_noisy", "log_d", "p_pred", "e_pred", "aug_d", "mel_len")
+    got = []
+    for i, (a, k) in enumerate(calls):
+        slot = pipe.submit(*a, **k)
+        if i >= 1:                                   # read batch i-1 while batch i is in flight (its slot is not reused yet)
+            pslot = (i - 1) % pipe.slots
+            pipe.done(pslot).synchronize()
+            o = mg.flatten_outputs(pipe.outputs(pslot))
+            got.append({n: o[n].clone() for n in keys})
+    pipe.done(slot).synchronize()
+    o = mg.flatten_outputs(pipe.outputs(slot))
+    got.append({n: o[n].clone() for n in keys})
+    torch.cuda.synchronize()
+    for i in range(len(calls)):
+        for n in keys:
+            assert torch.equal(got[i][n], eager[i][n]), (i, n)

@@ -61,7 +61,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=["bf16", "f16", "f32"])
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_conv1d(cuda, case, dtype, impl):
     ops = _ops()
@@ -111,9 +111,9 @@ def test_conv1d(cuda, case, dtype, impl):
         got, got_dot = got
     # tolerance: operands are identical, so only accumulation order (and tf32 operand rounding) differs
     tol_acc = 2e-3 if (dtype == torch.float32 and impl == "tc") else 2e-5
-    tol_out = tol_acc + (8e-3 if dtype == torch.bfloat16 else 0.0)    # bf16 storage of the result
-    if kw.get("ln") and dtype == torch.bfloat16 and impl == "simt":
-        tol_out += 2e-2                                                # simt stages pre-LN rows in bf16
+    tol_out = tol_acc + {torch.bfloat16: 8e-3, torch.float16: 1e-3}.get(dtype, 0.0)    # 16-bit storage of the result
+    if kw.get("ln") and dtype != torch.float32 and impl == "simt":
+        tol_out += 2e-2 if dtype == torch.bfloat16 else 2.5e-3         # simt stages pre-LN rows in the storage type
     if vt is not None:
         assert rel_err(got, ref[..., :512]) < tol_out
         assert rel_err(vt[:, :, :T].transpose(1, 2), ref[..., 512:]) < tol_out
@@ -226,7 +226,7 @@ def test_conv1d_tc_cta_pairs(cuda, case):
     assert torch.equal(pair, single), "the pair form accumulates in the same order as the single-CTA form"
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=["bf16", "f16", "f32"])
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("T", [128, 200, 520])
 @pytest.mark.parametrize("v_layout", ["transposed", "rowmajor"])
@@ -257,11 +257,11 @@ def test_attention(cuda, dtype, impl, T, v_layout):
                             impl=ops.IMPL_SIMT if impl == "simt" else ops.IMPL_TC)
     torch.cuda.synchronize()
     tol = {("simt", torch.float32): 2e-5, ("simt", torch.bfloat16): 8e-3, ("tc", torch.float32): 3e-3,
-           ("tc", torch.bfloat16): 1.5e-2}[(impl, dtype)]
+           ("tc", torch.bfloat16): 1.5e-2, ("simt", torch.float16): 1e-3, ("tc", torch.float16): 2e-3}[(impl, dtype)]
     assert rel_err(got, ref) < tol
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=["bf16", "f16", "f32"])
 def test_attention_tc_edge_lengths_and_rising_max(cuda, dtype):
     """Key-padding edge cases of the tensor-core kernel (a key half of a tile with no valid key, one valid key,
     exact tile boundaries) and scores whose row maximum keeps growing from key tile to key tile, so the lazily
@@ -280,7 +280,7 @@ def test_attention_tc_edge_lengths_and_rising_max(cuda, dtype):
     vv = vq.view(B, T, H, 64).permute(0, 2, 1, 3)
     s = (q @ k.transpose(-1, -2)).masked_fill(so.mask_from_lengths(lens, T)[:, None, None, :], float("-inf"))
     ref = (torch.softmax(s, -1) @ vv).permute(0, 2, 1, 3).reshape(B, T, 256)
-    if dtype == torch.bfloat16:
+    if dtype != torch.float32:
         got = ops.attention(torch.cat([qk, v], dim=-1).to(cuda, dtype), None, lens.to(cuda), H, impl=ops.IMPL_TC)
     else:
         Tp = (T + 63) // 64 * 64
@@ -290,7 +290,7 @@ def test_attention_tc_edge_lengths_and_rising_max(cuda, dtype):
     torch.cuda.synchronize()
     assert torch.isfinite(got.float()).all()
     # f32 runs as tf32 on the tensor pipe: operand rounding (2^-11) times scores of magnitude ~40 -> percent-level p error
-    tol = 1.5e-2 if dtype == torch.bfloat16 else 2e-2
+    tol = {torch.bfloat16: 1.5e-2, torch.float16: 3e-3}.get(dtype, 2e-2)
     for b in range(B):
         assert rel_err(got[b], ref[b]) < tol, (b, int(lens[b]))
 
@@ -420,6 +420,68 @@ def test_bilstm(cuda, H, Cin):
         ops.conv1d(cur, wih.unsqueeze(0).contiguous().to(cuda), b.to(cuda), out_f32=gx, want_out=False, impl=ops.IMPL_SIMT)
         cur = ops.bilstm_layer(gx, whh.contiguous().to(cuda), torch.float32)
     assert rel_err(cur, ref) < 2e-5
+
+
+@pytest.mark.parametrize("H", [80, 64])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+def test_bilstm_multi_utterance_form_is_bitwise_the_single_form(cuda, H, dtype):
+    """Four utterances per CTA (batches >= 16, LSTM_MULTI) run the same arithmetic in the same order as one utterance per CTA;
+    B = 18 leaves a partial last CTA (two absent utterances)."""
+    from styler_b200 import _lib
+    ops = _ops()
+    g = torch.Generator().manual_seed(17)
+    B, Ln = 18, 37
+    gx = torch.randn(B, Ln, 8 * H, generator=g).to(cuda)
+    whh = (torch.randn(2, 4 * H, H, generator=g) * 0.2).to(cuda)
+    try:
+        _lib.set_tuning("LSTM_MMA", 0)
+        _lib.set_tuning("LSTM_MULTI", 0)
+        single = ops.bilstm_layer(gx, whh, dtype)
+        _lib.set_tuning("LSTM_MULTI", 1)
+        multi = ops.bilstm_layer(gx, whh, dtype)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_tuning("LSTM_MULTI", -1)
+        _lib.set_tuning("LSTM_MMA", -1)
+    assert torch.isfinite(multi.float()).all()
+    assert torch.equal(single, multi)
+
+
+@pytest.mark.parametrize("H", [80, 64])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("B", [18, 150])        # 8 utterances per CTA / 16 per CTA (more CTAs than SM slots otherwise)
+def test_bilstm_tensor_core_recurrence(cuda, H, dtype, B):
+    """mma.sync form of the recurrence (16-bit activations, sixteen utterances per CTA; B = 18 leaves a CTA with two utterances)
+    against the fp32 recurrence written out in torch on the same gx / W_hh (gate order i, f, g, o; gx in [dir][unit][gate] order),
+    and against the CUDA-core kernel.  h enters the product rounded to the activation type -> storage-type tolerance."""
+    from styler_b200 import _lib
+    ops = _ops()
+    g = torch.Generator().manual_seed(19)
+    Ln = 41
+    gx = torch.randn(B, Ln, 8 * H, generator=g)
+    whh = torch.randn(2, 4 * H, H, generator=g) * 0.2
+    ref = torch.zeros(B, Ln, 2 * H)
+    for d in range(2):
+        h, c = torch.zeros(B, H), torch.zeros(B, H)
+        steps = range(Ln - 1, -1, -1) if d else range(Ln)
+        for t in steps:
+            pre = gx[:, t, d * 4 * H:(d + 1) * 4 * H].view(B, H, 4) + (h @ whh[d].t()).view(B, 4, H).transpose(1, 2)
+            i_, f_, g_, o_ = torch.sigmoid(pre[..., 0]), torch.sigmoid(pre[..., 1]), torch.tanh(pre[..., 2]), torch.sigmoid(pre[..., 3])
+            c = f_ * c + i_ * g_
+            h = o_ * torch.tanh(c)
+            ref[:, t, d * H:(d + 1) * H] = h
+    try:
+        _lib.set_tuning("LSTM_MMA", 1)
+        got = ops.bilstm_layer(gx.to(cuda), whh.to(cuda), dtype)
+        _lib.set_tuning("LSTM_MMA", 0)
+        simt = ops.bilstm_layer(gx.to(cuda), whh.to(cuda), dtype)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_tuning("LSTM_MMA", -1)
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 2e-3
+    assert torch.isfinite(got.float()).all()
+    assert rel_err(simt, ref) < tol
+    assert rel_err(got, ref) < tol, rel_err(got, ref)
 
 
 def test_classifier_tail_duration(cuda):

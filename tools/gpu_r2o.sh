@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests/test_forward_gpu.py tests/test_kernels_gpu.py tests/test_inspection_gpu.py -m gpu -q > $O/r2o_tests.log 2>&1; echo "pytest rc=$?" >> $O/r2o_tests.log
+grep -E "passed|failed|FAILED|ERROR|rc=" $O/r2o_tests.log | tail -15
+for P in 0 1; do
+  timeout 300 python bench.py --steps 30 --no-cpu-baseline --no-extras --pipeline $P > $O/r2o_bench_p$P.json 2>$O/r2o_bench_p$P.err
+  python -c "import json;d=json.load(open('$O/r2o_bench_p$P.json'));print('pipeline $P: value ms',d['ms_per_step'],'e2e ms',d['e2e']['ms_per_step'], d['clocks'])" || tail -5 $O/r2o_bench_p$P.err
+done
+STYLER_LSTM_MULTI=0 timeout 300 python bench.py --steps 30 --no-cpu-baseline --no-extras --pipeline 0 > $O/r2o_bench_lstm0.json 2>$O/r2o_bench_lstm0.err
+python -c "import json;d=json.load(open('$O/r2o_bench_lstm0.json'));print('lstm_multi=0: value ms',d['ms_per_step'])"
+timeout 300 python tools/timeline.py --csv $O/r2o_timeline.csv > $O/r2o_timeline.txt 2>&1; head -1 $O/r2o_timeline.txt
+timeout 300 python tools/timeline.py --precision fp16 > $O/r2o_timeline_fp16.txt 2>&1; head -1 $O/r2o_timeline_fp16.txt
+timeout 200 python tools/prof_kernels.py --only bilstm_h80 2>&1 | tail -3
