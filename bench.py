@@ -806,6 +806,32 @@ def main():
     if world == 1 and not args.no_extras:
         torch.cuda.synchronize()
         del graphs[:]
+        # every side measurement starts after a short idle period: the main legs leave the board at its power cap, and a leg that
+        # starts there runs at the sustained clock (MEASURED_PEAKS clocks_under_load ~1.3 GHz), not at the clock of the headline
+        time.sleep(2.0)
+        if pipe is None and use_graph:
+            # the two-stage batch pipeline (model.PipelinedSTYLER) on the same workload, device-resident, same timing rules
+            pp = PipelinedSTYLER(model, *split(resident[0]), slots=2)
+            for i in range(4):
+                pp.load_inputs(i % 2, *split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
+                pp.run(i % 2)
+            pp.join()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                pp.load_inputs(i % 2, *split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
+                pp.run(i % 2)
+            pp.join()
+            e1.record()
+            torch.cuda.synchronize()
+            msp = e0.elapsed_time(e1) / args.steps
+            extras["pipelined_two_stage"] = {"ms_per_step": msp, "value": frames_per_step / (msp * 1e-3), "unit": "mel-frames/s",
+                                             "steps": args.steps,
+                                             "note": "PipelinedSTYLER: style encoders + variance adaptor of batch i+1 on a low-priority stream "
+                                                     "under decoder + PostNet of batch i (two batches in flight); results bitwise those of forward()"}
+            del pp
+            torch.cuda.empty_cache()
         pipe = None
         for other in [m_ for m_ in ("fp16", "tf32", "bf16") if m_ != args.precision]:
             m2 = STYLER(precision=other)
@@ -815,6 +841,7 @@ def main():
             for _ in range(3):
                 m2(*a0, **k0)
             torch.cuda.synchronize()
+            time.sleep(2.0)
             n2 = min(args.steps, 10)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
