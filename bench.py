@@ -809,6 +809,13 @@ def main():
         # every side measurement starts after a short idle period: the main legs leave the board at its power cap, and a leg that
         # starts there runs at the sustained clock (MEASURED_PEAKS clocks_under_load ~1.3 GHz), not at the clock of the headline
         time.sleep(2.0)
+        xclk = ClockSampler(local)                   # SM clock under each side leg, next to its number
+        xclk.__enter__()
+
+        def leg_clock():
+            time.sleep(0.12)
+            c = xclk.summary()
+            return {"sm_mhz": c.get("sm_mhz"), "reasons": c.get("reasons")}
         if pipe is None and use_graph:
             # the two-stage batch pipeline (model.PipelinedSTYLER) on the same workload, device-resident, same timing rules
             pp = PipelinedSTYLER(model, *split(resident[0]), slots=2)
@@ -818,6 +825,7 @@ def main():
             pp.join()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            xclk.mark()
             e0.record()
             for i in range(args.steps):
                 pp.load_inputs(i % 2, *split(resident[i % NBUF])[0], **split(resident[i % NBUF])[1])
@@ -827,7 +835,7 @@ def main():
             torch.cuda.synchronize()
             msp = e0.elapsed_time(e1) / args.steps
             extras["pipelined_two_stage"] = {"ms_per_step": msp, "value": frames_per_step / (msp * 1e-3), "unit": "mel-frames/s",
-                                             "steps": args.steps,
+                                             "steps": args.steps, "clocks": leg_clock(),
                                              "note": "PipelinedSTYLER: style encoders + variance adaptor of batch i+1 on a low-priority stream "
                                                      "under decoder + PostNet of batch i (two batches in flight); results bitwise those of forward()"}
             del pp
@@ -842,8 +850,9 @@ def main():
                 m2(*a0, **k0)
             torch.cuda.synchronize()
             time.sleep(2.0)
-            n2 = min(args.steps, 10)
+            n2 = min(args.steps, 20)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            xclk.mark()
             e0.record()
             for i in range(n2):
                 a, kw = split(resident[i % NBUF])
@@ -852,8 +861,9 @@ def main():
             torch.cuda.synchronize()
             ms2 = e0.elapsed_time(e1) / n2
             extras[other + "_same_workload"] = {
-                "ms_per_step": ms2, "value": frames_per_step / (ms2 * 1e-3), "unit": "mel-frames/s", "steps": n2,
-                "note": "device-resident, eager launches, no batch pipelining; " +
+                "ms_per_step": ms2, "value": frames_per_step / (ms2 * 1e-3), "unit": "mel-frames/s", "steps": n2, "clocks": leg_clock(),
+                "note": "device-resident, eager launches, no batch pipelining; a leg that starts on a board already at its power cap runs "
+                        "at the sustained SM clock (see clocks), the stand-alone `bench.py --precision ...` run at the burst clock; " +
                         {"tf32": "fp32 storage + tcgen05 kind::tf32; meets the 1e-3 fp32 tolerance on the mels",
                          "fp16": "IEEE-half storage + tcgen05 kind::f16 (the bf16 kernels, 11-bit significand); meets the 1e-3 fp32 "
                                  "tolerance on the mels (tests/test_forward_gpu.py, same gates as tf32)",
@@ -886,6 +896,7 @@ def main():
                                             "note": "BASELINE configs[0] on the GPU: one utterance, 50 phonemes -> 400 frames, free-running; "
                                                     "wall clock per call incl. synchronize; eager has one host read of max(mel_len)"}
         del g1, m1
+        xclk.__exit__()
 
     if peer or push:
         torch.cuda.synchronize()

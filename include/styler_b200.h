@@ -287,6 +287,25 @@ int styler_set_tuning(const char* name, int32_t value);
  * capacity_ctas CTAs writes 8 clock64() phase stamps per CTA into it (tools/phase_timing.py); NULL disables. */
 int styler_debug_set_phase_buffer(int64_t* buf, int32_t capacity_ctas);
 
+/* ---- Losses of evaluate.py / train.py (loss.py:16-66): STYLERLoss.forward, cal_mel_loss, DomainAdversarialTrainingLoss ----
+ * One deterministic two-stage reduction over tensors read in place (the reference materialises seven masked_select copies):
+ *   out[0] = mean over kept (b,t), all n_mel channels of (mel - mel_target)^2          (nn.MSELoss, loss.py:21)
+ *   out[1] = the same for mel_postnet                                                  (loss.py:22)
+ *   out[2] = mean over kept (b,l) of |log_d_pred - log_d_target|                       (nn.L1Loss, loss.py:41)
+ *   out[3], out[4] = mean over kept (b,t) of |p_pred - p_target|, |e_pred - e_target|  (loss.py:42-43)
+ *   out[5] = sum of the three nn.NLLLoss means, -mean_b post_x[b][aug_label[b]]        (loss.py:45-47, 61-64)
+ *   out[6], out[7] = number of kept mel rows / source positions
+ * mel* fp32 [B][T][n_mel] contiguous; *_keep bool (uint8) [B][T] / [B][L] with 1 = KEEP (the callers pass ~mel_mask, ~src_mask);
+ * log_d*, fp32 [B][L]; p*, e* fp32 [B][T]; post_* fp32 [B][2] log-probabilities; aug_label int64 [B].  Every group may be NULL
+ * (cal_mel_loss: only the mel group; DAT loss: only the posteriors); its outputs are then 0 / nan as an empty selection is in torch.
+ * workspace: styler_loss_workspace_bytes() bytes. */
+int64_t styler_loss_workspace_bytes(void);
+int styler_loss_fwd(const float* mel, const float* mel_postnet, const float* mel_target, const uint8_t* mel_keep,
+                    const float* log_d_pred, const float* log_d_target, const uint8_t* src_keep, const float* p_pred,
+                    const float* p_target, const float* e_pred, const float* e_target, const float* post_d, const float* post_p,
+                    const float* post_e, const int64_t* aug_label, int32_t B, int32_t T, int32_t L, int32_t n_mel,
+                    void* workspace, int64_t workspace_bytes, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

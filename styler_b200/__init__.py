@@ -2,7 +2,7 @@
 and the TacotronSTFT mel front end, behind the reference's Python surface.  See DESIGN.md / INTEGRATION.md."""
 from . import _lib  # noqa: F401
 
-__all__ = ["STYLER", "GraphedSTYLER", "PipelinedSTYLER", "TacotronSTFT", "Generator", "ReferenceFrontEnd", "ops", "hparams"]
+__all__ = ["STYLER", "GraphedSTYLER", "PipelinedSTYLER", "TacotronSTFT", "Generator", "ReferenceFrontEnd", "STYLERLoss", "DomainAdversarialTrainingLoss", "ops", "hparams"]
 
 
 def __getattr__(name):
@@ -24,7 +24,10 @@ def __getattr__(name):
     if name == "ReferenceFrontEnd":
         from .frontend import ReferenceFrontEnd
         return ReferenceFrontEnd
-    if name in ("ops", "hparams", "model", "stft", "engine", "dist", "vocoder", "frontend"):
+    if name in ("STYLERLoss", "DomainAdversarialTrainingLoss"):    # loss.py drop-ins (forward values; evaluate.py:88-104)
+        from . import loss as _loss
+        return getattr(_loss, name)
+    if name in ("ops", "hparams", "model", "stft", "engine", "dist", "vocoder", "frontend", "loss"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -119,6 +119,8 @@ _SIGNATURES = {
     "styler_decoder_workspace_bytes": [ctypes.POINTER(DecoderWeights), c_i32, c_i32, c_i32],
     "styler_decoder_fwd": [ctypes.POINTER(DecoderWeights), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
                            c_vp, c_i64, c_vp],
+    "styler_loss_workspace_bytes": [],
+    "styler_loss_fwd": [c_vp] * 15 + [c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp],
     "styler_peer_alloc": [c_i64, ctypes.POINTER(c_vp), c_vp],
     "styler_peer_open": [c_vp, ctypes.POINTER(c_vp)],
     "styler_peer_close": [c_vp],
@@ -150,7 +152,8 @@ def lib():
     h.styler_launch_count.restype = ctypes.c_int64
     h.styler_fftblock_workspace_bytes.restype = ctypes.c_int64
     h.styler_debug_trace_dump.restype = ctypes.c_int64
-    for name in ("styler_predictor_workspace_bytes", "styler_postnet_workspace_bytes", "styler_decoder_workspace_bytes"):
+    for name in ("styler_predictor_workspace_bytes", "styler_postnet_workspace_bytes", "styler_decoder_workspace_bytes",
+                 "styler_loss_workspace_bytes"):
         getattr(h, name).restype = ctypes.c_int64
     _lib = h
     return h
