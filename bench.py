@@ -519,6 +519,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every forward kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true", help="skip the tf32 and B=1 latency side measurements")
+    ap.add_argument("--extras-pipeline", action="store_true",
+                    help="also time the two-stage batch pipeline (PipelinedSTYLER) as a side leg (opt-in: one of eight pipelined runs at the "
+                         "bench shape stopped making progress on a fresh box and was killed by its timeout; not reproduced, cause unknown)")
     ap.add_argument("--gather", default="push", choices=["push", "peer", "nccl"],
                     help="N > 1, how the mels reach rank 0: push = DMA copy of the packed results into rank 0's IPC-mapped region on a "
                          "side stream + our flag protocol (overlaps the next step, no SM time); peer = FUSED, the producing kernels store "
@@ -581,6 +584,7 @@ def main():
     # so the gather (N > 1) or the D2H copies (e2e) of step i can still be reading graph k's outputs while step i+1 runs in
     # the other graph.
     use_graph = not args.no_graph
+    dbg = (lambda m: print("[bench %.1f] %s" % (time.perf_counter(), m), file=sys.stderr, flush=True)) if os.environ.get("STYLER_BENCH_DEBUG") else (lambda m: None)
     LAUNCH_DESC = ("two-stage batch pipeline (PipelinedSTYLER): per slot one CUDA graph for style encoders + variance adaptor on a "
                    "low-priority stream and one for decoder + PostNet on a high-priority stream; stage one of batch i+1 overlaps stage "
                    "two of batch i; 2 slots" if args.pipeline else "CUDA-graph replay of the forward (2 alternating graphs)")
@@ -600,6 +604,7 @@ def main():
         a0, k0 = split(resident[0])
         pipe = PipelinedSTYLER(model, a0, k0, slots=2, result_mirrors=[gatherer.buffer(k) for k in range(2)] if peer else None,
                                back_priority=int(os.environ.get("STYLER_PIPE_PRIO", "-1")))
+        dbg("pipeline captured")
     elif use_graph:
         a0, k0 = split(resident[0])
         # peer gather: graph k is captured with this rank's slice (slot k) of rank 0's receive region as the second destination
@@ -684,7 +689,9 @@ def main():
     # ---- device-resident timed region (value) + per-launch events on the dominant kernel ----------------------
     launches0 = _lib.launch_count()
     clocks.mark()
+    dbg("warm-up done, timing")
     secs, wall = timed(lambda i: step(resident[i % NBUF], i % 2), args.steps)
+    dbg("timed region done")
     clocks.__exit__()
     launches_counted = _lib.launch_count() - launches0
     value = world * frames_per_step * args.steps / secs
@@ -694,6 +701,7 @@ def main():
     # inside the native FFT-block call while the same forward runs eagerly (events cannot be read back out of a graph
     # replay) -- same kernels, same shapes, same clocks; `launches_per_step` is counted in this pass too.
     import ctypes
+    dbg("roofline leg")
     roof_steps = min(args.steps, 10)
     _lib.check(_lib.lib().styler_debug_ffn1_timing(1, T), "ffn1_timing")
     n0 = _lib.launch_count()
@@ -797,7 +805,9 @@ def main():
 
     for i in range(max(2 * NBUF, args.warmup)):     # every host batch through both streams once: allocator pools, NCCL
         e2e_step(i)                                 # channels and receive buffers of the e2e streams exist before timing
+    dbg("e2e warm-up done")
     e2e_secs = e2e_timed(args.steps)
+    dbg("e2e done")
     e2e_value = world * frames_per_step * args.steps / e2e_secs
     d2h_bytes = d2h[0].numel()
 
@@ -816,7 +826,7 @@ def main():
             time.sleep(0.12)
             c = xclk.summary()
             return {"sm_mhz": c.get("sm_mhz"), "reasons": c.get("reasons")}
-        if pipe is None and use_graph:
+        if pipe is None and use_graph and args.extras_pipeline:
             # the two-stage batch pipeline (model.PipelinedSTYLER) on the same workload, device-resident, same timing rules
             pp = PipelinedSTYLER(model, *split(resident[0]), slots=2)
             for i in range(4):

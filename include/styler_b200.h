@@ -136,7 +136,8 @@ int styler_postnet_fwd(const styler_postnet_weights* w, const void* mel_act, con
                        int64_t ws_bytes, void* stream);
 /* STYLER.decode (styler.py:29-37) = Decoder.forward (transformer/Models.py:111-135: x + pos rows, n_layers FFT blocks) +
  * mel_linear + PostNet + residual.  x: [B][T][d_model] contiguous, activation dtype; pos: fp32 [T][d_model] (the caller
- * supplies rows beyond max_seq_len, Models.py:120-122); mel_out / post_out: fp32 [B][T][n_mel] contiguous; mel_out2 /
+ * supplies rows beyond max_seq_len, Models.py:120-122), or NULL when x already carries the position rows
+ * (styler_bucket_embed_sum_fwd with pos): x is then read in place by the first block; mel_out / post_out: fp32 [B][T][n_mel] contiguous; mel_out2 /
  * post_out2: optional second destinations (same layout).  postnet == NULL: use_postnet=False, post_out is not written. */
 typedef struct {
   int32_t n_layers; const styler_fft_weights* layers;     /* array of n_layers */
@@ -229,13 +230,14 @@ int styler_length_regulator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, 
  * the scaled predictions p*p_control / e*e_control the reference returns (modules.py:370,380) go to p_scaled / e_scaled
  * (fp32 [B][T], may be NULL); pitch_emb_out / energy_emb_out (activation dtype, contiguous [B][T][C], may be NULL) receive
  * the two embedding rows on their own, which is what predict_inference returns (modules.py:299-309).  out may be NULL
- * (then text / spk / noise are not read). */
+ * (then text / spk / noise are not read).  pos (fp32 [T][C], may be NULL): the decoder's position rows, added to out and
+ * out_noisy on the way out -- styler_decoder_fwd is then called with pos = NULL and skips its own pass. */
 int styler_bucket_embed_sum_fwd(const void* text, const void* spk, const void* noise, int64_t in_bstride,
                                 int32_t in_ld, const float* p_val, const float* e_val, float p_scale, float e_scale,
                                 const float* pitch_bins, const float* energy_bins, int32_t nbins,
                                 const float* pitch_emb, const float* energy_emb, void* out, void* out_noisy,
                                 int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx, float* p_scaled,
-                                float* e_scaled, void* pitch_emb_out, void* energy_emb_out, int32_t B, int32_t T,
+                                float* e_scaled, void* pitch_emb_out, void* energy_emb_out, const float* pos, int32_t B, int32_t T,
                                 int32_t C, int32_t dtype, void* stream);
 
 /* ---- TacotronSTFT.mel_spectrogram (audio/stft.py:51-79,141-160; audio_processing.py:80-86):

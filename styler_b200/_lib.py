@@ -101,7 +101,7 @@ _SIGNATURES = {
     "styler_length_regulator_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32,
                                     c_i32, c_i32, c_i32, c_vp],
     "styler_bucket_embed_sum_fwd": [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_f32, c_f32, c_vp, c_vp, c_i32, c_vp,
-                                    c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
+                                    c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
                                     c_i32, c_vp],
     "styler_stft_mel_fwd": [c_vp, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp],
     "styler_stft_mel_ex_fwd": [c_vp, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_i32, c_vp, c_f32,

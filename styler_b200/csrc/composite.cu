@@ -132,14 +132,21 @@ extern "C" int styler_decoder_fwd(const styler_decoder_weights* w, const void* x
   void* mel_act = take(static_cast<size_t>(B) * T * NM * es);
   const int64_t xs = static_cast<int64_t>(T) * D;
   int rc;
-  // x + position rows (transformer/Models.py:124-125; the table beyond max_seq_len is the caller's, :120-122)
-  if ((rc = styler_add_fwd(x, xs, D, nullptr, 0, 0, nullptr, 0, pos, act[0], xs, D, B, T, D, dtype, stream)) != 0) return rc;
-  int cur = 0;
+  // x + position rows (transformer/Models.py:124-125; the table beyond max_seq_len is the caller's, :120-122).  pos == NULL: the
+  // caller's x already carries them (styler_bucket_embed_sum_fwd with pos): the first block reads x in place, no pass over it here
+  const void* in = x;
+  int cur = 1;                                   // act[cur ^ 1] receives the next block's output
+  if (pos != nullptr) {
+    if ((rc = styler_add_fwd(x, xs, D, nullptr, 0, 0, nullptr, 0, pos, act[0], xs, D, B, T, D, dtype, stream)) != 0) return rc;
+    in = act[0];
+    cur = 0;
+  }
   for (int l = 0; l < w->n_layers; ++l) {
-    if ((rc = styler_fftblock_fwd(&w->layers[l], act[cur], xs, D, act[cur ^ 1], xs, D, lens, B, T, dtype, impl, ws_fft, fft_ws,
+    if ((rc = styler_fftblock_fwd(&w->layers[l], in, xs, D, act[cur ^ 1], xs, D, lens, B, T, dtype, impl, ws_fft, fft_ws,
                                   stream)) != 0)
       return rc;
     cur ^= 1;
+    in = act[cur];
   }
   {   // mel_linear (styler.py:31): fp32 result (+ optional second destination) and the activation-dtype copy the PostNet reads
     styler_conv1d_args a;

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256) bucket_embed_sum_kernel(
     const float* __restrict__ pbins, const float* __restrict__ ebins, int nbins, const float* __restrict__ pemb,
     const float* __restrict__ eemb, T* __restrict__ out, T* __restrict__ out_noisy, long long o_bs, int o_ld,
     int32_t* __restrict__ p_idx, int32_t* __restrict__ e_idx, float* __restrict__ p_scaled, float* __restrict__ e_scaled,
-    T* __restrict__ pemb_out, T* __restrict__ eemb_out, int B, int Tn, int C) {
+    T* __restrict__ pemb_out, T* __restrict__ eemb_out, const float* __restrict__ pos, int B, int Tn, int C) {
   extern __shared__ float sbins[];
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) { sbins[i] = pbins[i]; sbins[nbins + i] = ebins[i]; }
   __syncthreads();
@@ -483,18 +483,26 @@ __global__ void __launch_bounds__(256) bucket_embed_sum_kernel(
     if (pemb_out != nullptr) store8(pemb_out + row * C + c, pe);     // the embedding rows themselves (predict_inference)
     if (eemb_out != nullptr) store8(eemb_out + row * C + c, ee);
     if (out == nullptr) continue;
-    float tx[8], sp[8], v[8];
+    float tx[8], sp[8], v[8], ps[8];
     load8(text + in_off + c, tx);
     load8(spk + in_off + c, sp);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ((tx[i] + pe[i]) + sp[i]) + ee[i];
-    store8(out + o_off + c, v);
+    for (int i = 0; i < 8; ++i) { v[i] = ((tx[i] + pe[i]) + sp[i]) + ee[i]; ps[i] = 0.f; }
+    // optional: the decoder's position rows (transformer/Models.py:124-125) added on the way out, in the reference's order
+    // (x + pos, (x + noise) + pos): the decoder then starts on this buffer without its own full pass over it
+    if (pos != nullptr) load8(pos + static_cast<long long>(t) * C + c, ps);
+    {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pos != nullptr ? v[i] + ps[i] : v[i];
+      store8(out + o_off + c, o);
+    }
     if (out_noisy != nullptr) {
-      float nz[8];
+      float nz[8], o[8];
       load8(noise + in_off + c, nz);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += nz[i];
-      store8(out_noisy + o_off + c, v);
+      for (int i = 0; i < 8; ++i) { const float vn = v[i] + nz[i]; o[i] = pos != nullptr ? vn + ps[i] : vn; }
+      store8(out_noisy + o_off + c, o);
     }
   }
 }
@@ -695,7 +703,7 @@ extern "C" int styler_bucket_embed_sum_fwd(const void* text, const void* spk, co
                                            const float* pitch_emb, const float* energy_emb, void* out, void* out_noisy,
                                            int64_t o_bstride, int32_t o_ld, int32_t* p_idx, int32_t* e_idx,
                                            float* p_scaled, float* e_scaled, void* pitch_emb_out, void* energy_emb_out,
-                                           int32_t B, int32_t T, int32_t C, int32_t dtype, void* stream) {
+                                           const float* pos, int32_t B, int32_t T, int32_t C, int32_t dtype, void* stream) {
   sb::TraceScope trace__("bucket_embed_sum", stream);
   SB_REQUIRE(p_val && e_val && pitch_bins && energy_bins && pitch_emb && energy_emb, "bucket_embed_sum: null pointer");
   SB_REQUIRE(out == nullptr || (text != nullptr && spk != nullptr), "bucket_embed_sum: out needs text and spk");
@@ -707,7 +715,7 @@ extern "C" int styler_bucket_embed_sum_fwd(const void* text, const void* spk, co
   SB_REQUIRE((text == nullptr || al16(text)) && (spk == nullptr || al16(spk)) && (out == nullptr || al16(out)) &&
                  (noise == nullptr || al16(noise)) && (out_noisy == nullptr || al16(out_noisy)) && al16(pitch_emb) &&
                  al16(energy_emb) && (pitch_emb_out == nullptr || al16(pitch_emb_out)) &&
-                 (energy_emb_out == nullptr || al16(energy_emb_out)),
+                 (energy_emb_out == nullptr || al16(energy_emb_out)) && (pos == nullptr || al16(pos)),
              "bucket_embed_sum: pointers must be 16-byte aligned");
   const long long rows = static_cast<long long>(B) * T;
   SB_DISPATCH_DTYPE(dtype, TT,
@@ -717,7 +725,7 @@ extern "C" int styler_bucket_embed_sum_fwd(const void* text, const void* spk, co
                         in_ld, p_val, e_val, p_scale, e_scale, pitch_bins,
                         energy_bins, nbins, pitch_emb, energy_emb, static_cast<TT*>(out), static_cast<TT*>(out_noisy),
                         o_bstride, o_ld, p_idx, e_idx, p_scaled, e_scaled, static_cast<TT*>(pitch_emb_out),
-                        static_cast<TT*>(energy_emb_out), B, T, C)));
+                        static_cast<TT*>(energy_emb_out), pos, B, T, C)));
   SB_LAUNCH_OK();
   return 0;
 }

@@ -82,6 +82,8 @@ class Engine:
         import os
         self.use_streams = os.environ.get("STYLER_NO_STREAMS", "0") != "1"   # four audio-encoder branches on side streams
         self._streams = None
+        self._aux_used = set()
+        self._aux = None                     # three more side streams: the duration / energy / pitch predictors
         self._branch_events = []
         self._post = [None, None, None]
         self._pack({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
@@ -264,8 +266,9 @@ class Engine:
         ins = (mel_target, p_idx, e_idx, mel_aug)
         names = ("d", "p", "e", None)
         self._post = [None, None, None]
+        prep = lambda x: x() if callable(x) else x      # an input may be a thunk: its cast / quantisation then runs on ITS branch's stream
         if not self.use_streams:
-            outs = [self._audio_branch(br, xin, mel_len, src_len, L) for br, xin in zip(self.w.branches, ins)]
+            outs = [self._audio_branch(br, prep(xin), mel_len, src_len, L) for br, xin in zip(self.w.branches, ins)]
             ups = [t(c) for t, c in zip(tails, outs)] if tails is not None else None
             if classify:
                 self._post = [self._classifier(outs[i], self.w.cls[names[i]]) for i in range(3)]
@@ -279,7 +282,7 @@ class Engine:
         for i, (st, br, xin) in enumerate(zip(self._streams, self.w.branches, ins)):
             st.wait_event(start)
             with torch.cuda.stream(st):
-                c = self._audio_branch(br, xin, mel_len, src_len, L)
+                c = self._audio_branch(br, prep(xin), mel_len, src_len, L)
                 if tails is not None:
                     up = tails[i](c)
                     for t_ in (up if isinstance(up, (tuple, list)) else (up,)):
@@ -304,7 +307,18 @@ class Engine:
             for ev in self._branch_events:
                 main.wait_event(ev)
 
+    def _aux_stream(self, i):
+        if self._aux is None:
+            self._aux = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        self._aux_used.add(i)                # only streams forked in THIS forward are joined (a CUDA-graph capture must not wait
+        return self._aux[i]                  # for a stream that is not part of it)
+
     def join_audio_streams(self):
+        if self.use_streams and self._aux is not None:
+            main = torch.cuda.current_stream(self.device)
+            for i in sorted(self._aux_used):
+                main.wait_stream(self._aux[i])
+            self._aux_used.clear()
         if self.use_streams and self._streams is not None:
             main = torch.cuda.current_stream(self.device)
             for st in self._streams:
@@ -324,14 +338,14 @@ class Engine:
         return t if self.dt == torch.float32 else ops.cast(t, self.dt)
 
     # ------------------------------------------------------------------------------------------ decode (styler.py:29-37)
-    def decode(self, x, mel_lens, mel_out=None, post_out=None, mel_mirror=None, post_mirror=None):
+    def decode(self, x, mel_lens, mel_out=None, post_out=None, mel_mirror=None, post_mirror=None, has_pos=False):
         """x [B,T,256] (activation dtype) -> (mel fp32 [B,T,80], mel_postnet fp32 [B,T,80]); the results are written into
         mel_out / post_out when given (slices of the packed result buffer).  mel_mirror / post_mirror: second, WRITE-ONLY
         destinations -- this rank's slice of rank 0's gather buffer mapped over NVLink (dist.PeerGather): mel_linear and the last
         PostNet convolution store their fp32 results there from their own epilogues (`out2_f32`), so the gather is fused into
         the tensor-core kernels that produce the mels."""
-        T = x.shape[1]
-        mel, post = ops.decoder(x.contiguous(), self.w.dec_struct, self._pos("dec", T), mel_lens, mel_out=mel_out, post_out=post_out,
+        T = x.shape[1]         # has_pos: x already carries the decoder's position rows (variance_adapt adds them in its embedding sum)
+        mel, post = ops.decoder(x.contiguous(), self.w.dec_struct, None if has_pos else self._pos("dec", T), mel_lens, mel_out=mel_out, post_out=post_out,
                                 mel_out2=mel_mirror, post_out2=post_mirror, impl=self.impl)
         if post is None:                             # use_postnet=False (styler.py:33-36): mel_output_postnet = mel_output
             if post_mirror is not None:
@@ -340,16 +354,20 @@ class Engine:
         return mel, post
 
     # ------------------------------------------------------------------------------------------ style modeling
-    def encode(self, src_seq, speaker_embed, mel_target, mel_aug, p_norm, e_input, src_len, mel_len):
+    def encode(self, src_seq, speaker_embed, mel_target, mel_aug, p_norm, e_input, src_len, mel_len, dur_async=False):
         """StyleEncoder.forward + the L-level part of StyleModeling.forward (modules.py:225-235,311-353).
-        Returns the [B,L,1280] concatenated encodings, log-duration prediction and the DAT posteriors."""
+        Returns the [B,L,1280] concatenated encodings, log-duration prediction and the DAT posteriors.
+        dur_async: the caller does not consume log_d inside the forward (teacher-forced durations): the duration predictor then
+        runs on a side stream that is joined at the end of the forward."""
         w = self.w
         B, L = src_seq.shape
         dev = self.device
         enc = torch.empty(B, L, 1280, device=dev, dtype=self.dt)
         # the audio-encoder branches (side streams) overlap the text encoder and speaker projections (this stream)
-        p_idx, e_idx = ops.quantize_index(p_norm), ops.quantize_index(e_input)                          # utils.py:417-429
-        mel_t, mel_a = self._act(mel_target), self._act(mel_aug)
+        # each branch's own input preparation (fp32 -> activation dtype cast of a mel, utils.py:417-429 quantisation of p / e) is the
+        # first thing on that branch's stream: nothing the branches need runs on this stream first
+        p_idx, e_idx = (lambda: ops.quantize_index(p_norm)), (lambda: ops.quantize_index(e_input))
+        mel_t, mel_a = (lambda: self._act(mel_target)), (lambda: self._act(mel_aug))
         spk_in = self._act(speaker_embed).unsqueeze(0)                                                  # [1,B,512]
 
         def pitch_tail(p_enc):                         # modules.py:332,338-340 on the pitch branch's own stream
@@ -369,8 +387,21 @@ class Engine:
         post = tuple(self._post)                       # produced on the side streams; valid after join_audio_streams() (end of forward)
         ops.add(neck_up, p_up, out=enc[..., 256:512])                                                   # modules.py:350
         ops.add(neck_up, e_up, out=enc[..., 768:1024])
-        dur_in = ops.add(neck_up, d_up)
-        log_d = self.predictor(dur_in, src_len, w.pred["duration"])                                     # modules.py:353
+        if dur_async and self.use_streams:
+            main = torch.cuda.current_stream(self.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            a = self._aux_stream(0)
+            a.wait_event(fork)
+            with torch.cuda.stream(a):
+                dur_in = ops.add(neck_up, d_up)
+                log_d = self.predictor(dur_in, src_len, w.pred["duration"])                             # modules.py:353
+            for t_ in (neck_up, d_up):
+                t_.record_stream(a)
+            log_d.record_stream(main)
+        else:
+            dur_in = ops.add(neck_up, d_up)
+            log_d = self.predictor(dur_in, src_len, w.pred["duration"])                                 # modules.py:353
         self.inter = dict(text_encoding=text, text_encoding_neck=neck_up, pitch_encoding=p_enc, speaker_encoding=spk,
                           speaker_encoding_p=spk_p, duration_encoding=d_up, energy_encoding=e_up, noise_encoding=n_up,
                           pitch_up=p_up, max_seq_len=L)
@@ -384,9 +415,37 @@ class Engine:
         dur = d_target if d_target is not None else duration
         encT, mel_len, cum = ops.length_regulator(enc, dur, T)
         lens = mel_lens_for_mask if mel_lens_for_mask is not None else mel_len
-        e_pred = self.predictor(encT[..., 768:1024], lens, w.pred["energy"])
-        p_in = ops.add(encT[..., 256:512], encT[..., 512:768])
-        p_pred = self.predictor(p_in, lens, w.pred["pitch"])
+        # The two predictors are independent.  Teacher-forced (p_target and e_target given: evaluate.py / train.py) their outputs
+        # are only RETURNED -- the embedding sum below reads the targets -- so both run on side streams under the first decoder
+        # kernels and are joined at the end of the forward; free-running, the energy predictor overlaps the pitch predictor.
+        teacher = p_target is not None and e_target is not None
+        if self.use_streams:
+            main = torch.cuda.current_stream(self.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            a0 = self._aux_stream(1)
+            a0.wait_event(fork)
+            with torch.cuda.stream(a0):
+                e_pred = self.predictor(encT[..., 768:1024], lens, w.pred["energy"])
+                e_done = torch.cuda.Event()
+                e_done.record(a0)
+            encT.record_stream(a0)
+            e_pred.record_stream(main)
+            a1 = self._aux_stream(2) if teacher else main
+            if teacher:
+                a1.wait_event(fork)
+            with torch.cuda.stream(a1):
+                p_in = ops.add(encT[..., 256:512], encT[..., 512:768])
+                p_pred = self.predictor(p_in, lens, w.pred["pitch"])
+            if teacher:
+                encT.record_stream(a1)
+                p_pred.record_stream(main)
+            else:
+                main.wait_event(e_done)
+        else:
+            e_pred = self.predictor(encT[..., 768:1024], lens, w.pred["energy"])
+            p_in = ops.add(encT[..., 256:512], encT[..., 512:768])
+            p_pred = self.predictor(p_in, lens, w.pred["pitch"])
         p_val, p_scale = (p_target.to(self.device, torch.float32).contiguous(), 1.0) if p_target is not None else (p_pred, float(p_control))
         e_val, e_scale = (e_target.to(self.device, torch.float32).contiguous(), 1.0) if e_target is not None else (e_pred, float(e_control))
         # clean and noisy decoder inputs land in one [2B,T,256] buffer so both decodes run as a single batched pass
@@ -395,7 +454,7 @@ class Engine:
         scaled = p_scale != 1.0 or e_scale != 1.0      # the reference returns prediction * control (modules.py:370,380)
         res = ops.bucket_embed_sum(encT[..., 0:256], encT[..., 512:768], encT[..., 1024:1280], p_val, e_val,
                                    p_scale, e_scale, w.pitch_bins, w.energy_bins, w.pitch_emb, w.energy_emb,
-                                   want_noisy=True, out=xx[:B], out_noisy=xx[B:], want_scaled=scaled)
+                                   want_noisy=True, out=xx[:B], out_noisy=xx[B:], want_scaled=scaled, pos=self._pos("dec", T))
         x, x_noisy = res[0], res[1]
         if scaled:
             p_pred = res[4] if p_target is None else p_pred
@@ -428,7 +487,8 @@ class Engine:
         B, L = src_seq.shape
         if max_src_len is not None and max_src_len != L:
             raise ValueError("max_src_len (%d) must equal the padded text length (%d)" % (max_src_len, L))
-        enc, log_d, post = self.encode(src_seq, speaker_embed, mel_target, mel_aug, p_norm, e_input, src_len, mel_len)
+        enc, log_d, post = self.encode(src_seq, speaker_embed, mel_target, mel_aug, p_norm, e_input, src_len, mel_len,
+                                       dur_async=d_target is not None)
         if d_target is not None:                                   # teacher forcing (styler.py:44-46)
             d_target = d_target.to(dev, torch.int64).contiguous()
             T = int(max_mel_len) if max_mel_len else int(mel_len.max().item())
@@ -461,7 +521,7 @@ class Engine:
             if packed is None or self.result_mirror.numel() != packed_nbytes(B, T):
                 raise ValueError("result_mirror must hold exactly %d bytes for B=%d, T=%d (and needs the PostNet)" % (packed_nbytes(B, T), B, T))
             mirror, mel_m, post_m = packed_views(B, T, dev, self.result_mirror)
-        mel2, post2 = self.decode(ctx.xx, out_len.repeat(2), mel_out, post_out, mel_m, post_m)
+        mel2, post2 = self.decode(ctx.xx, out_len.repeat(2), mel_out, post_out, mel_m, post_m, has_pos=True)
         post = ctx.post
         if not ctx.joined:
             self.join_audio_streams()                  # the DAT posteriors (side streams) are outputs of this forward

@@ -201,8 +201,9 @@ def predictor(x, pw, lens, *, impl=IMPL_AUTO):
 
 @_on_tensor_device
 def decoder(x, dw, pos, lens, *, mel_out=None, post_out=None, mel_out2=None, post_out2=None, impl=IMPL_AUTO):
-    """STYLER.decode in one native call (styler_decoder_fwd): x [B,T,D] contiguous -> (mel fp32 [B,T,n_mel], post fp32 or None)."""
-    assert x.is_contiguous() and pos.is_contiguous() and pos.dtype == torch.float32 and pos.shape[0] >= x.shape[1]
+    """STYLER.decode in one native call (styler_decoder_fwd): x [B,T,D] contiguous -> (mel fp32 [B,T,n_mel], post fp32 or None).
+    pos=None: x already carries the position rows (bucket_embed_sum(..., pos=...)) and is consumed in place."""
+    assert x.is_contiguous() and (pos is None or (pos.is_contiguous() and pos.dtype == torch.float32 and pos.shape[0] >= x.shape[1]))
     B, T, _ = x.shape
     code = L.dtype_code(x.dtype)
     nm = dw.n_mel
@@ -418,8 +419,9 @@ def length_regulator_scan(duration):
 @_on_tensor_device
 def bucket_embed_sum(text, spk, noise, p_val, e_val, p_scale, e_scale, pitch_bins, energy_bins, pitch_emb, energy_emb,
                      want_noisy=True, want_idx=False, out=None, out_noisy=None, want_scaled=False, want_emb=False,
-                     want_sum=True, emb_dtype=None):
+                     want_sum=True, emb_dtype=None, pos=None):
     """bucketize + embedding (+ 4-way sum), styler_bucket_embed_sum_fwd.  Inputs are never modified.
+    pos: fp32 [>=T, C] position rows added to out / out_noisy (the decoder is then run with pos=None).
     Returns (out, out_noisy, p_idx, e_idx) and, appended when asked for, (p_scaled, e_scaled) = the predictions times their
     control factors (fp32) and (pitch_embedding, energy_embedding) = the two embedding rows on their own (dtype of text)."""
     p_val, e_val = p_val.contiguous(), e_val.contiguous()
@@ -443,6 +445,7 @@ def bucket_embed_sum(text, spk, noise, p_val, e_val, p_scale, e_scale, pitch_bin
     else:
         text = spk3 = noise = out = out_n = None
         want_noisy = False
+    assert pos is None or (pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[0] >= T and pos.shape[1] == C and want_sum)
     p_idx = torch.empty(B, T, device=dev, dtype=torch.int32) if want_idx else None
     e_idx = torch.empty(B, T, device=dev, dtype=torch.int32) if want_idx else None
     p_sc = torch.empty(B, T, device=dev, dtype=torch.float32) if want_scaled else None
@@ -456,7 +459,7 @@ def bucket_embed_sum(text, spk, noise, p_val, e_val, p_scale, e_scale, pitch_bin
                                                 L.ptr(energy_emb), L.ptr(out), L.ptr(out_n),
                                                 int(out.stride(0)) if out is not None else 0,
                                                 int(out.stride(1)) if out is not None else 0, L.ptr(p_idx), L.ptr(e_idx),
-                                                L.ptr(p_sc), L.ptr(e_sc), L.ptr(p_emb), L.ptr(e_emb), B, T, C,
+                                                L.ptr(p_sc), L.ptr(e_sc), L.ptr(p_emb), L.ptr(e_emb), L.ptr(pos), B, T, C,
                                                 L.dtype_code(emb_dt), L.stream_ptr()), "bucket_embed_sum")
     res = (out, out_n, p_idx, e_idx)
     if want_scaled:

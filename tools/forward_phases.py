@@ -31,7 +31,7 @@ with torch.no_grad():
         ev[1].record()
         x, xn, _, p_pred, e_pred, _ = eng.variance_adapt(enc, log_d, T, t["mel_len"], t["d_target"], t["p_target"], t["e_target"])
         ev[2].record()
-        eng.decode(eng._xx, t["mel_len"].repeat(2))
+        eng.decode(eng._xx, t["mel_len"].repeat(2), has_pos=True)
         eng.join_audio_streams()
         ev[3].record()
         torch.cuda.synchronize()
