@@ -197,6 +197,12 @@ int styler_groupnorm_relu_fwd(void* x, int64_t bstride, int32_t ld, const float*
 int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const int64_t* mel_len,
                               const int64_t* src_len, void* out, int64_t o_bstride, int32_t o_ld, int32_t B,
                               int32_t Tr, int32_t L, int32_t C, int32_t dtype, void* stream);
+/* GroupNorm (+affine, ReLU; statistics from the producing conv's gn_partial sums, as styler_groupnorm_relu_partial_fwd) applied
+ * while the Mel Calibrator reads the frames: x is the RAW conv output and is not modified; the normalised tensor never exists. */
+int styler_gn_calibrator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const float* gamma, const float* beta,
+                             const float* partial, int32_t n_part, float* stats_ws, const int64_t* mel_len, const int64_t* src_len,
+                             void* out, int64_t o_bstride, int32_t o_ld, int32_t B, int32_t Tr, int32_t L, int32_t C, float eps,
+                             int32_t dtype, void* stream);
 
 /* ---- One layer of a bidirectional LSTM over the padded grid (modules.py:179-182; nn.LSTM, gates i,f,g,o).
  * gx: fp32 [B][L][2][H][4] = x @ W_ih^T + (b_ih + b_hh) in QUAD order: direction (fwd, rev), hidden unit, gate (i,f,g,o)

@@ -95,6 +95,8 @@ _SIGNATURES = {
     "styler_groupnorm_relu_partial_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp],
     "styler_mel_calibrator_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
                                   c_i32, c_vp],
+    "styler_gn_calibrator_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32,
+                                 c_i32, c_f32, c_i32, c_vp],
     "styler_bilstm_layer_fwd": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "styler_classifier_tail_fwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
     "styler_duration_round_fwd": [c_vp, c_vp, c_i64, c_f32, c_f32, c_vp],

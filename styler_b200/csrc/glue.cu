@@ -268,10 +268,14 @@ __global__ void gn_apply_relu_kernel(T* __restrict__ x, long long bs, int ld, co
 }
 
 // ---------------------------------------------------------------------------------------- Mel Calibrator
-template <typename T>
+// GN: x is the RAW output of the branch's last convolution; GroupNorm (16 channels per group, statistics from gn_finalize) +
+// affine + ReLU (modules.py:113-117) are applied to every frame as it is read, so the normalised [B,Tr,C] tensor is never
+// written (one read of x instead of a read-modify-write pass plus this read; frames beyond mel_len are never touched).
+template <typename T, bool GN>
 __global__ void mel_calibrator_kernel(const T* __restrict__ x, long long x_bs, int x_ld, const int64_t* __restrict__ mel_len,
                                       const int64_t* __restrict__ src_len, T* __restrict__ out, long long o_bs, int o_ld,
-                                      int B, int Tr, int L, int C) {
+                                      int B, int Tr, int L, int C, const float* __restrict__ stats,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta) {
   const int per_row = C / 8;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<long long>(B) * L * per_row) return;
@@ -284,15 +288,31 @@ __global__ void mel_calibrator_kernel(const T* __restrict__ x, long long x_bs, i
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const T* xb = x + b * x_bs + c;
+  float sc[8], sh[8];                            // GN: v -> relu(v * sc + sh), sc = rstd * gamma, sh = beta - mean * rstd * gamma
+  if constexpr (GN) {
+    const int g = b * (C / 16) + c / 16;
+    const float mean = stats[2 * g], rstd = stats[2 * g + 1];
+    load8(gamma + c, sc);
+    load8(beta + c, sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] *= rstd; sh[i] = fmaf(-mean, sc[i], sh[i]); }
+  }
+  auto load_frame = [&](int t, float (&v)[8]) {
+    load8(xb + static_cast<long long>(t) * x_ld, v);
+    if constexpr (GN) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f);
+    }
+  };
   if (l < sl && ml > 0) {
     if (ml == sl) {
-      load8(xb + static_cast<long long>(l) * x_ld, acc);
+      load_frame(l, acc);
     } else if (ml > sl) {                        // compression: mean over segment l (get_scale(ml, sl))
       const int q = ml / sl, r = ml % sl;
       const int start = l * q + (l < r ? l : r), size = q + (l < r ? 1 : 0);
       for (int k = 0; k < size; ++k) {
         float v[8];
-        load8(xb + static_cast<long long>(start + k) * x_ld, v);
+        load_frame(start + k, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += v[i];
       }
@@ -303,7 +323,7 @@ __global__ void mel_calibrator_kernel(const T* __restrict__ x, long long x_bs, i
       const int q = sl / ml, r = sl % ml;
       const int boundary = r * (q + 1);
       const int i = l < boundary ? l / (q + 1) : r + (l - boundary) / q;
-      load8(xb + static_cast<long long>(i) * x_ld, acc);
+      load_frame(i, acc);
     }
   }
   store8(out + b * o_bs + static_cast<long long>(l) * o_ld + c, acc);
@@ -642,9 +662,31 @@ extern "C" int styler_mel_calibrator_fwd(const void* x, int64_t x_bstride, int32
   SB_REQUIRE(B > 0 && Tr > 0 && L > 0 && C % 8 == 0 && x_ld % 8 == 0 && o_ld % 8 == 0 && x_bstride % 8 == 0 &&
                  o_bstride % 8 == 0 && al16(x) && al16(out), "mel_calibrator: bad shape/alignment");
   const long long n = static_cast<long long>(B) * L * (C / 8);
-  SB_DISPATCH_DTYPE(dtype, TT, (mel_calibrator_kernel<TT><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  SB_DISPATCH_DTYPE(dtype, TT, (mel_calibrator_kernel<TT, false><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                                    static_cast<const TT*>(x), x_bstride, x_ld, mel_len, src_len, static_cast<TT*>(out),
-                                   o_bstride, o_ld, B, Tr, L, C)));
+                                   o_bstride, o_ld, B, Tr, L, C, nullptr, nullptr, nullptr)));
+  SB_LAUNCH_OK();
+  return 0;
+}
+
+// GroupNorm (statistics from the producing conv's gn_partial sums) + ReLU + Mel Calibrator in one pass over the raw conv output.
+extern "C" int styler_gn_calibrator_fwd(const void* x, int64_t x_bstride, int32_t x_ld, const float* gamma, const float* beta,
+                                        const float* partial, int32_t n_part, float* stats_ws, const int64_t* mel_len,
+                                        const int64_t* src_len, void* out, int64_t o_bstride, int32_t o_ld, int32_t B, int32_t Tr,
+                                        int32_t L, int32_t C, float eps, int32_t dtype, void* stream) {
+  sb::TraceScope trace__("gn_calibrator", stream);
+  SB_REQUIRE(x && gamma && beta && partial && stats_ws && mel_len && src_len && out, "gn_calibrator: null pointer");
+  SB_REQUIRE(B > 0 && Tr > 0 && L > 0 && C % 16 == 0 && x_ld % 8 == 0 && o_ld % 8 == 0 && x_bstride % 8 == 0 && o_bstride % 8 == 0 &&
+                 al16(x) && al16(out) && al16(gamma) && al16(beta) && n_part == (Tr + 127) / 128,
+             "gn_calibrator: bad shape/alignment (n_part must be ceil(Tr/128))");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int groups = C / 16;
+  gn_finalize_kernel<<<blocks_for(static_cast<long long>(B) * groups, 128), 128, 0, s>>>(partial, stats_ws, B, groups, n_part, Tr, eps);
+  SB_LAUNCH_OK();
+  const long long n = static_cast<long long>(B) * L * (C / 8);
+  SB_DISPATCH_DTYPE(dtype, TT, (mel_calibrator_kernel<TT, true><<<blocks_for(n, 256), 256, 0, s>>>(
+                                   static_cast<const TT*>(x), x_bstride, x_ld, mel_len, src_len, static_cast<TT*>(out), o_bstride, o_ld,
+                                   B, Tr, L, C, stats_ws, gamma, beta)));
   SB_LAUNCH_OK();
   return 0;
 }

@@ -230,6 +230,8 @@ class Engine:
 
     def _audio_branch(self, br, xin, mel_len, src_len, L):
         x = None
+        c = None
+        last = len(br.convs) - 1
         for j, (cw, cb, g, be) in enumerate(br.convs):
             if j == 0 and br.onehot:
                 x = ops.onehot_conv(xin, cw, cb, self.dt)
@@ -241,11 +243,15 @@ class Engine:
                 # tensor-core conv: the GroupNorm statistics come out of its epilogue (no separate pass over the tensor)
                 part = torch.empty(B, (Tr + 127) // 128, N // 16, 2, device=src.device, dtype=torch.float32)
                 x = ops.conv1d(src, cw, cb, pad=2, impl=IMPL_TC, gn_partial=part)
-                ops.groupnorm_relu_partial_(x, g, be, part, 1e-5)
+                if j == last:      # the last GroupNorm + ReLU is applied by the Mel Calibrator as it reads the frames
+                    c = ops.gn_calibrator(x, g, be, part, mel_len, src_len, L, 1e-5)
+                else:
+                    ops.groupnorm_relu_partial_(x, g, be, part, 1e-5)
             else:
                 x = ops.conv1d(src, cw, cb, pad=2, impl=self.impl)
                 ops.groupnorm_relu_(x, g, be, 16, 1e-5)
-        c = ops.mel_calibrator(x, mel_len, src_len, L)
+        if c is None:
+            c = ops.mel_calibrator(x, mel_len, src_len, L)
         for (wih, bias, whh) in br.lstm:
             B = c.shape[0]
             gx = torch.empty(B, L, wih.shape[1], device=c.device, dtype=torch.float32)

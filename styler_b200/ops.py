@@ -346,6 +346,22 @@ def mel_calibrator(x, mel_len, src_len, Lmax, out=None):
     return out
 
 
+@_on_tensor_device
+def gn_calibrator(x, gamma, beta, partial, mel_len, src_len, Lmax, eps=1e-5, out=None):
+    """GroupNorm(16 channels per group, statistics from the producing conv's `partial`) + ReLU + Mel Calibrator in one pass over
+    the RAW conv output x (not modified): styler_gn_calibrator_fwd."""
+    x, x_bs, x_ld = _v3(x, "x")
+    B, Tr, C = x.shape
+    if out is None:
+        out = torch.empty(B, Lmax, C, device=x.device, dtype=x.dtype)
+    o, o_bs, o_ld = _v3(out, "out")
+    ws = torch.empty(B * (C // 16) * 2, device=x.device, dtype=torch.float32)
+    L.check(L.lib().styler_gn_calibrator_fwd(L.ptr(x), x_bs, x_ld, L.ptr(gamma), L.ptr(beta), L.ptr(partial), partial.shape[1], L.ptr(ws),
+                                             L.ptr(mel_len), L.ptr(src_len), L.ptr(o), o_bs, o_ld, B, Tr, Lmax, C, eps,
+                                             L.dtype_code(x.dtype), L.stream_ptr()), "gn_calibrator")
+    return out
+
+
 def lstm_quad_order(H):
     """Row permutation that takes the stacked input projection [W_ih_fwd ; W_ih_rev] (PyTorch order [dir][gate i,f,g,o][unit])
     to the order the BiLSTM kernel reads gx in: [dir][unit][gate] -- the four gates of a unit are adjacent, element t of a

@@ -1,8 +1,12 @@
-"""Child-process body of tests/test_forward_gpu.py::test_pipelined_batches_match_eager (run as `python -m tests.pipeline_case`)."""
-import torch
+"""Child-process body of tests/test_forward_gpu.py::test_pipelined_batches_match_eager (run as `python tests/pipeline_case.py`)."""
+import os
+import sys
 
-from oracle import make_golden as mg
-from oracle import styler_oracle as so
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from oracle import make_golden as mg  # noqa: E402
+from oracle import styler_oracle as so  # noqa: E402
 
 
 def main():

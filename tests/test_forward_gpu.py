@@ -297,5 +297,5 @@ def test_pipelined_batches_match_eager(cuda):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "tests.pipeline_case"], cwd=root, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "pipeline_case.py")], cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PIPELINE_CASE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

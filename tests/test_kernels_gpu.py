@@ -399,6 +399,34 @@ def test_mel_calibrator(cuda):
     assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+def test_gn_calibrator_fused(cuda, dtype):
+    """GroupNorm + ReLU applied inside the Mel Calibrator (raw conv output in, normalised tensor never written) against the
+    CPU statement F.group_norm -> relu -> mel_calibrator, and against the two-pass kernels; compress / equal / expand lengths."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    B, Tr, Cin, C, Lm = 5, 200, 64, 320, 40
+    x = torch.randn(B, Tr, Cin, generator=g)
+    w = (torch.rand(5, C, Cin, generator=g) * 2 - 1) / math.sqrt(5 * Cin)
+    bias = torch.randn(C, generator=g) * 0.1
+    gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    mel_len = torch.tensor([200, 40, 13, 193, 41])
+    src_len = torch.tensor([40, 40, 40, 7, 39])
+    xd, wd = x.to(cuda, dtype), w.to(cuda, dtype)
+    part = torch.empty(B, (Tr + 127) // 128, C // 16, 2, device=cuda, dtype=torch.float32)
+    y = ops.conv1d(xd, wd, bias.to(cuda), pad=2, impl=ops.IMPL_TC, gn_partial=part)
+    raw = y.clone()
+    fused = ops.gn_calibrator(y, gamma.to(cuda), beta.to(cuda), part, mel_len.to(cuda), src_len.to(cuda), Lm)
+    assert torch.equal(y, raw), "the raw conv output must not be modified"
+    two = ops.mel_calibrator(ops.groupnorm_relu_partial_(y, gamma.to(cuda), beta.to(cuda), part), mel_len.to(cuda), src_len.to(cuda), Lm)
+    torch.cuda.synchronize()
+    yr = raw.float().cpu()                                           # GroupNorm over the padded Tr grid, 16 channels per group
+    ref = so.mel_calibrator(F.relu(F.group_norm(yr.transpose(1, 2), C // 16, gamma, beta, 1e-5)).transpose(1, 2), mel_len, src_len)
+    tol = {torch.float32: 2e-5, torch.bfloat16: 8e-3, torch.float16: 1e-3}[dtype]
+    assert rel_err(fused, ref) < tol, rel_err(fused, ref)
+    assert rel_err(two, ref) < 2 * tol
+
+
 @pytest.mark.parametrize("H,Cin", [(80, 256), (64, 320)])
 def test_bilstm(cuda, H, Cin):
     ops = _ops()
