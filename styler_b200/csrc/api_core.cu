@@ -60,11 +60,13 @@ struct TuneDef { const char* name; int dflt, lo, hi; };
 // ATTN_PERSIST: persistent attention CTAs (0 | 1);  TC_WIDE: full-width N tile (two MMAs per k-step) for 256 < N <= 512;
 // LSTM_MULTI: four utterances per BiLSTM CTA for batches >= 16 (0 | 1);  ATTN_POLY: eighths of the softmax exponentials computed
 // by an FMA-pipe polynomial instead of MUFU.EX2 (0 | 2 | 3 | 4; 16-bit operands);  LSTM_MMA: BiLSTM recurrence on mma.sync,
-// sixteen utterances per CTA (16-bit activations, batches >= 8)
+// sixteen utterances per CTA (16-bit activations, batches >= 8);  STFT_OCC: STFT shape with three CTAs per SM (16 frames per CTA,
+// magnitudes aliased onto the FFT exchange buffer: 1) or two CTAs of twelve warps (24 frames per CTA: 2) instead of two CTAs of
+// eight warps (0); bitwise-equal results
 const TuneDef kTune[TUNE_COUNT] = {{"TC_2CTA", 1, 0, 2}, {"TC_PERSIST", 1, 0, 2}, {"CONV_WIN", 1, 0, 1}, {"TC_BN", 0, 0, 256},
                                    {"TC_SMEM_KB", 113, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}, {"TC_WIDE", 1, 0, 1},
                                    {"LSTM_MULTI", 0, 0, 1}, {"ATTN_POLY", 2, 0, 4},
-                                   {"LSTM_MMA", 1, 0, 1}};
+                                   {"LSTM_MMA", 1, 0, 1}, {"STFT_OCC", 1, 0, 2}};
 std::atomic<int> g_tune[TUNE_COUNT];          // 0 = not resolved yet, else value + 1
 }  // namespace
 

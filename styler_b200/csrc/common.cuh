@@ -41,7 +41,7 @@ int num_sms();   // SM count of the current device (cached per device)
 
 // A/B switches: read once from the environment (STYLER_<NAME>), overridable at run time through styler_set_tuning()
 // (tests and tools/prof_kernels.py flip them inside one process).
-enum Tuning { TUNE_TC_2CTA = 0, TUNE_TC_PERSIST, TUNE_CONV_WIN, TUNE_TC_BN, TUNE_TC_SMEM_KB, TUNE_PDL, TUNE_ATTN_PERSIST, TUNE_TC_WIDE, TUNE_LSTM_MULTI, TUNE_ATTN_POLY, TUNE_LSTM_MMA, TUNE_COUNT };
+enum Tuning { TUNE_TC_2CTA = 0, TUNE_TC_PERSIST, TUNE_CONV_WIN, TUNE_TC_BN, TUNE_TC_SMEM_KB, TUNE_PDL, TUNE_ATTN_PERSIST, TUNE_TC_WIDE, TUNE_LSTM_MULTI, TUNE_ATTN_POLY, TUNE_LSTM_MMA, TUNE_STFT_OCC, TUNE_COUNT };
 int tuning(Tuning t);
 
 #define SB_OPT_IN_SMEM(flags, kern, bytes)                                                                     \

@@ -13,12 +13,18 @@ namespace sb {
 namespace {
 
 constexpr int NFFT = 1024, HOP = 256, NBINS = 513, HALF = 512;
-constexpr int FPB = 32;                              // frames per CTA (one 128-byte run of every mel row)
-constexpr int kWarps = 8;                            // one frame per warp in flight, FPB / kWarps frames per warp
-constexpr int NSAMP = (FPB - 1) * HOP + NFFT;
 constexpr int WBUF = HALF + HALF / 16;               // complex work buffer per warp, skewed: slot(i) = i + (i >> 4)
 constexpr int MAGLD = NBINS + 3;
-constexpr int MELLD = FPB + 1;
+// Two shapes of the same arithmetic (bitwise-equal results, tests/test_kernels_gpu.py):
+//   <32, 8, 2, false>: 32 frames per CTA (one 128-byte run of every mel row), separate magnitude buffer, 107 KB of smem -> 2 CTAs
+//                   (16 warps) per SM, 116 registers;
+//   <16, 8, 3, true>:  16 frames per CTA, the magnitudes overwrite the warp's FFT exchange buffer (the split pass keeps its 18
+//                   results in registers across one __syncwarp), 70 KB of smem and <= 85 registers -> 3 CTAs (24 warps) per SM.
+//                   The kernel is latency-bound (issue slots 48 % busy at 4 warps per scheduler): the extra warps are the point.
+template <int FPB> struct StftShape {
+  static constexpr int NSAMP = (FPB - 1) * HOP + NFFT;
+  static constexpr int MELLD = FPB + 1;
+};
 constexpr int kBasisCap = 1536;                      // floats of smem for the non-zero bands of the mel basis (727 used by the
                                                      // reference's 80-mel Slaney basis); larger bases are read from global
 
@@ -73,21 +79,23 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 // One warp = one frame: 512-point complex Stockham FFT as three radix-8 passes (Ns = 1, 8, 64), each lane owning two
 // 8-point butterflies per pass held in registers; the passes exchange data through a per-warp smem buffer, so the only
 // synchronisation inside the transform is __syncwarp().
-__global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* __restrict__ y, int N, int F,
+template <int FPB, int KW, int MINB, bool ALIAS_MAG>
+__global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __restrict__ y, int N, int F,
                                                                   const float* __restrict__ basis,
                                                                   const int32_t* __restrict__ band, int n_mels,
                                                                   float* __restrict__ mel, float* __restrict__ energy,
                                                                   float in_scale, int clamp, int32_t* __restrict__ clip_flag,
                                                                   int frame_major, float* __restrict__ e_input, float e_min,
                                                                   float e_inv_range, const int64_t* __restrict__ n_samples) {
+  constexpr int NSAMP = StftShape<FPB>::NSAMP, MELLD = StftShape<FPB>::MELLD;
   extern __shared__ __align__(16) uint8_t stft_smem[];
   float2* tw = reinterpret_cast<float2*>(stft_smem);                       // W_1024^k, k < 512
   float2* twA = tw + HALF;                                                 // W_64^k,  k < 8   (pass-2 base twiddles)
   float2* twB = twA + 8;                                                   // W_512^k, k < 64  (pass-3 base twiddles)
-  float2* wbuf = twB + 64;                                                 // [kWarps][WBUF]
-  float* samp = reinterpret_cast<float*>(wbuf + kWarps * WBUF);            // [NSAMP]
-  float* mag = samp + NSAMP;                                               // [kWarps][MAGLD]
-  float* s_en = mag + kWarps * MAGLD;                                      // [FPB]
+  float2* wbuf = twB + 64;                                                 // [KW][WBUF]
+  float* samp = reinterpret_cast<float*>(wbuf + KW * WBUF);            // [NSAMP]
+  float* mag = samp + NSAMP;                                               // [KW][MAGLD] (absent when ALIAS_MAG)
+  float* s_en = mag + (ALIAS_MAG ? 0 : KW * MAGLD);                    // [FPB]
   float* s_basis = s_en + FPB;                                             // [kBasisCap] bands of the mel basis, back to back
   int* s_lo = reinterpret_cast<int*>(s_basis + kBasisCap);                 // [n_mels] first bin of the band
   int* s_hi = s_lo + n_mels;                                               // [n_mels] one past the last bin
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   const int Fb = n_samples != nullptr ? min(F, 1 + N / HOP) : F;
   if (f0 >= Fb) {   // block-uniform: this whole block of frames is padding
     const int nf = min(FPB, F - f0);
-    for (int i = threadIdx.x; i < n_mels * nf; i += kWarps * 32) {
+    for (int i = threadIdx.x; i < n_mels * nf; i += KW * 32) {
       if (frame_major) mel[(static_cast<long long>(b) * F + f0) * n_mels + i] = 0.f;
       else mel[(static_cast<long long>(b) * n_mels + i / nf) * F + f0 + i % nf] = 0.f;
     }
@@ -116,29 +124,49 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
     return;
   }
   bool clipped = false;
-  for (int i0 = 0; i0 < NSAMP; i0 += 4 * kWarps * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {                         // four independent loads in flight before anything is stored
-      const int i = i0 + u * kWarps * 32 + threadIdx.x;
-      int src = f0 * HOP + i - NFFT / 2;
-      if (src < 0) src = -src;
-      if (src >= N) src = 2 * (N - 1) - src;
-      v[u] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
+  auto scale_clamp = [&](float x) {
+    x *= in_scale;
+    if (clamp) {   // get_mel_from_wav(norm=False), audio/tools.py:44-49: clamp to [-1,1]; the flag only sees the NEGATIVE side
+      clipped |= x < -1.f;
+      x = fminf(fmaxf(x, -1.f), 1.f);
     }
+    return x;
+  };
+  // Sample window of the block.  Interior blocks (no reflection, 16-byte aligned start: all but the first / last two blocks of an
+  // utterance) issue ALL of their loads as float4 here, before the twiddle / band set-up below, and store them after it: one
+  // memory round trip per CTA (the scalar loop -- four loads in flight, NSAMP / 1024 round trips -- was 10-13 % of the kernel's
+  // warp-state samples on long-scoreboard waits, profiles/ncu_stft_r2l_packed.md).
+  constexpr int NV = NSAMP / 4, PER = (NV + KW * 32 - 1) / (KW * 32);
+  const int first = f0 * HOP - NFFT / 2;
+  const bool interior = first >= 0 && first + NSAMP <= N && (reinterpret_cast<uintptr_t>(yb + (first >= 0 ? first : 0)) & 15u) == 0;
+  float4 v4[PER];
+  if (interior) {
+    const float4* src4 = reinterpret_cast<const float4*>(yb + first);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kWarps * 32 + threadIdx.x;
-      float x = v[u] * in_scale;
-      if (clamp) {   // get_mel_from_wav(norm=False), audio/tools.py:44-49: clamp to [-1,1]; the flag only sees the NEGATIVE side
-        clipped |= x < -1.f;
-        x = fminf(fmaxf(x, -1.f), 1.f);
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * KW * 32 + threadIdx.x;
+      if (idx < NV) v4[u] = __ldg(src4 + idx);
+    }
+  } else {
+    for (int i0 = 0; i0 < NSAMP; i0 += 4 * KW * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                         // four independent loads in flight before anything is stored
+        const int i = i0 + u * KW * 32 + threadIdx.x;
+        int src = first + i;
+        if (src < 0) src = -src;
+        if (src >= N) src = 2 * (N - 1) - src;
+        v[u] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
       }
-      if (i < NSAMP) samp[i] = x;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * KW * 32 + threadIdx.x;
+        const float x = scale_clamp(v[u]);
+        if (i < NSAMP) samp[i] = x;
+      }
     }
   }
-  if (clipped && clip_flag != nullptr) clip_flag[b] = 1;   // one (benign, same-value) store per thread after the staging loop
-  for (int k = threadIdx.x; k < HALF; k += kWarps * 32) {
+  for (int k = threadIdx.x; k < HALF; k += KW * 32) {
     float sn, cs;
     sincospif(-static_cast<float>(k) / 512.0f, &sn, &cs);
     tw[k] = make_float2(cs, sn);
@@ -149,17 +177,40 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
     sincospif(-static_cast<float>(k) / (threadIdx.x < 8 ? 32.0f : 256.0f), &sn, &cs);
     (threadIdx.x < 8 ? twA : twB)[k] = make_float2(cs, sn);
   }
-  for (int m = threadIdx.x; m < n_mels; m += kWarps * 32) { s_lo[m] = band[2 * m]; s_hi[m] = band[2 * m + 1]; }
+  for (int m = threadIdx.x; m < n_mels; m += KW * 32) { s_lo[m] = band[2 * m]; s_hi[m] = band[2 * m + 1]; }
+  if (interior) {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * KW * 32 + threadIdx.x;
+      if (idx < NV) {
+        float4 x = v4[u];
+        x.x = scale_clamp(x.x); x.y = scale_clamp(x.y); x.z = scale_clamp(x.z); x.w = scale_clamp(x.w);
+        reinterpret_cast<float4*>(samp)[idx] = x;
+      }
+    }
+  }
+  if (clipped && clip_flag != nullptr) clip_flag[b] = 1;   // one (benign, same-value) store per thread after the staging
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int off = 0;
-    for (int m = 0; m < n_mels; ++m) { s_off[m] = off; off += s_hi[m] - s_lo[m]; }
-    s_off[n_mels] = off;
+  if (threadIdx.x < 32) {   // exclusive prefix of the band widths: warp scan, 32 rows at a time (a one-thread loop stalled the CTA)
+    int base = 0;
+    for (int m0 = 0; m0 < n_mels; m0 += 32) {
+      const int m = m0 + threadIdx.x;
+      const int w = m < n_mels ? s_hi[m] - s_lo[m] : 0;
+      int incl = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (static_cast<int>(threadIdx.x) >= o) incl += t;
+      }
+      if (m < n_mels) s_off[m] = base + incl - w;
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_off[n_mels] = base;
   }
   __syncthreads();
   const bool basis_in_smem = s_off[n_mels] <= kBasisCap;
   if (basis_in_smem) {
-    for (int m = threadIdx.x >> 5; m < n_mels; m += kWarps) {
+    for (int m = threadIdx.x >> 5; m < n_mels; m += KW) {
       const int lo = s_lo[m], w = s_hi[m] - lo;
       for (int i = threadIdx.x & 31; i < w; i += 32) s_basis[s_off[m] + i] = basis[static_cast<long long>(m) * NBINS + lo + i];
     }
@@ -168,9 +219,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* wb = wbuf + warp * WBUF;
-  float* mg = mag + warp * MAGLD;
+  float* mg = ALIAS_MAG ? reinterpret_cast<float*>(wb) : mag + warp * MAGLD;   // 513 floats; wb holds 2 * WBUF
   auto slot = [](int i) { return i + (i >> 4); };
-  for (int fl = warp; fl < FPB; fl += kWarps) {
+  for (int fl = warp; fl < FPB; fl += KW) {
     if (f0 + fl >= Fb) break;                   // warp-uniform
     float2 v[2][8];
     // ---- pass 1 (Ns = 1): window, pack z[n] = x[2n] + i x[2n+1], butterfly, no twiddles
@@ -227,20 +278,33 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
     // ---- split post-pass: X[k] = E + W^k * O.  Bins k and 512-k share Z[k], Z[512-k] and the twiddle
     // (E(512-k) = conj E(k), O(512-k) = conj O(k), W^(512-k) = -conj W^k), so each step yields two magnitudes.
     float esum = 0.f;
-    for (int k = lane; k <= HALF / 2; k += 32) {
-      const float2 zk = wb[slot(k & (HALF - 1))];
-      const float2 zr = wb[slot((HALF - k) & (HALF - 1))];
-      const float2 zc = make_float2(zr.x, -zr.y);                                        // conj(Z[512-k])
-      const float2 e = __fmul2_rn(cadd(zk, zc), make_float2(0.5f, 0.5f));                // E(k)
-      const float2 o = __fmul2_rn(mul_mi(csub(zk, zc)), make_float2(0.5f, 0.5f));        // O(k) = -i/2 (Z[k] - conj(Z[512-k]))
-      const float2 wo = cmul(o, tw[k]);
-      const float2 X = cadd(e, wo);                                                      // X[k]
-      const float2 Y = __fadd2_rn(make_float2(e.x, -e.y), make_float2(-wo.x, wo.y));     // X[512-k] = conj(E) - conj(W^k O)
-      const float2 pp = __ffma2_rn(make_float2(X.y, Y.y), make_float2(X.y, Y.y), __fmul2_rn(make_float2(X.x, Y.x), make_float2(X.x, Y.x)));
-      const float p0 = pp.x, p1 = pp.y;
-      mg[k] = sqrt_approx(p0);
-      mg[HALF - k] = sqrt_approx(p1);
-      esum += k == HALF / 2 ? p0 : p0 + p1;     // bin 256 is its own mirror
+    float mk[9], mm[9];                          // ALIAS_MAG: magnitudes of bins k / 512-k, parked until every lane has read wb
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+      const int k = lane + 32 * it;
+      if (k <= HALF / 2) {
+        const float2 zk = wb[slot(k & (HALF - 1))];
+        const float2 zr = wb[slot((HALF - k) & (HALF - 1))];
+        const float2 zc = make_float2(zr.x, -zr.y);                                        // conj(Z[512-k])
+        const float2 e = __fmul2_rn(cadd(zk, zc), make_float2(0.5f, 0.5f));                // E(k)
+        const float2 o = __fmul2_rn(mul_mi(csub(zk, zc)), make_float2(0.5f, 0.5f));        // O(k) = -i/2 (Z[k] - conj(Z[512-k]))
+        const float2 wo = cmul(o, tw[k]);
+        const float2 X = cadd(e, wo);                                                      // X[k]
+        const float2 Y = __fadd2_rn(make_float2(e.x, -e.y), make_float2(-wo.x, wo.y));     // X[512-k] = conj(E) - conj(W^k O)
+        const float2 pp = __ffma2_rn(make_float2(X.y, Y.y), make_float2(X.y, Y.y), __fmul2_rn(make_float2(X.x, Y.x), make_float2(X.x, Y.x)));
+        const float p0 = pp.x, p1 = pp.y;
+        if (ALIAS_MAG) { mk[it] = sqrt_approx(p0); mm[it] = sqrt_approx(p1); }
+        else { mg[k] = sqrt_approx(p0); mg[HALF - k] = sqrt_approx(p1); }
+        esum += k == HALF / 2 ? p0 : p0 + p1;     // bin 256 is its own mirror
+      }
+    }
+    if (ALIAS_MAG) {
+      __syncwarp();                              // all of wb consumed: the magnitudes may land on it
+#pragma unroll
+      for (int it = 0; it < 9; ++it) {
+        const int k = lane + 32 * it;
+        if (k <= HALF / 2) { mg[k] = mk[it]; mg[HALF - k] = mm[it]; }
+      }
     }
     esum = warp_sum(esum);                      // energy: L2 norm over the 513 bins (stft.py:158)
     if (lane == 0) s_en[fl] = sqrtf(esum);
@@ -256,7 +320,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
         const float* br = basis + static_cast<long long>(m) * NBINS;
         for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(br + k), mg[k], acc);
       }
-      s_mel[m * MELLD + fl] = logf(fmaxf(acc, 1e-5f));
+      s_mel[m * MELLD + fl] = __logf(fmaxf(acc, 1e-5f));   // MUFU.LG2 form: |error| < 2e-6 on [1e-5, 1e4]
     }
     __syncwarp();                               // mg / wb are reused by this warp's next frame
   }
@@ -265,12 +329,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
   const int nf = min(FPB, F - f0);
   const int nv = min(FPB, Fb - f0);            // valid frames of this block; [nv, nf) is per-utterance padding -> zeros
   if (frame_major) {   // [B][F][n_mels]: the channel-last layout STYLER.forward takes as mel_target (the reference stores mel.T)
-    for (int i = threadIdx.x; i < n_mels * nf; i += kWarps * 32) {
+    for (int i = threadIdx.x; i < n_mels * nf; i += KW * 32) {
       const int fl = i / n_mels, m = i % n_mels;
       mel[(static_cast<long long>(b) * F + f0 + fl) * n_mels + m] = fl < nv ? s_mel[m * MELLD + fl] : 0.f;
     }
   } else {
-    for (int i = threadIdx.x; i < n_mels * FPB; i += kWarps * 32) {
+    for (int i = threadIdx.x; i < n_mels * FPB; i += KW * 32) {
       const int m = i / FPB, fl = i % FPB;
       if (fl < nf) mel[(static_cast<long long>(b) * n_mels + m) * F + f0 + fl] = fl < nv ? s_mel[m * MELLD + fl] : 0.f;
     }
@@ -283,6 +347,26 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft_mel_kernel(const float* _
       e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = ok ? fminf(fmaxf((e - e_min) * e_inv_range, 0.f), 1.f) : 0.f;
   }
 }
+
+
+template <int FPB, int KW, int MINB, bool ALIAS_MAG> struct StftLaunch {
+  static size_t smem_bytes(int n_mels) {
+    return sizeof(float2) * (HALF + 8 + 64) + sizeof(float2) * KW * WBUF + sizeof(float) * StftShape<FPB>::NSAMP +
+           (ALIAS_MAG ? 0 : sizeof(float) * KW * MAGLD) + sizeof(float) * FPB + sizeof(float) * kBasisCap +
+           sizeof(int) * (3 * n_mels + 1) + sizeof(float) * n_mels * StftShape<FPB>::MELLD;
+  }
+  static constexpr size_t kSmemCap = (228 * 1024 - MINB * 1024) / MINB / 1024 * 1024;   // MINB CTAs per SM, 1 KB reserved each
+  static int run(const float* y, int B, int N, int F, const float* basis, const int32_t* band, int n_mels, float* mel,
+                 float* energy, float in_scale, int clamp, int32_t* clip_flag, int frame_major, float* e_input, float e_min,
+                 float e_inv, const int64_t* n_samples, cudaStream_t s) {
+    static DeviceFlags attr_set;
+    SB_OPT_IN_SMEM(attr_set, (stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG>), kSmemCap);
+    stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG><<<dim3(ceil_div(F, FPB), B), KW * 32, smem_bytes(n_mels), s>>>(
+        y, N, F, basis, band, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min, e_inv, n_samples);
+    SB_LAUNCH_OK();
+    return 0;
+  }
+};
 
 }  // namespace
 }  // namespace sb
@@ -300,18 +384,21 @@ extern "C" int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, cons
   if (clip_flag != nullptr) SB_CUDA_OK(cudaMemsetAsync(clip_flag, 0, sizeof(int32_t) * B, s));
   mel_band_kernel<<<ceil_div(n_mels, 8), 256, 0, s>>>(mel_basis, n_mels, band_ws);
   SB_LAUNCH_OK();
-  dim3 grid(ceil_div(F, FPB), B);
-  const size_t smem = sizeof(float2) * (HALF + 8 + 64) + sizeof(float2) * kWarps * WBUF + sizeof(float) * NSAMP +
-                      sizeof(float) * kWarps * MAGLD + sizeof(float) * FPB + sizeof(float) * kBasisCap +
-                      sizeof(int) * (3 * n_mels + 1) + sizeof(float) * n_mels * MELLD;
-  SB_REQUIRE(smem <= 113 * 1024, "stft_mel: n_mels=%d needs %zu bytes of shared memory", n_mels, smem);
-  static DeviceFlags attr_set;
-  SB_OPT_IN_SMEM(attr_set, stft_mel_kernel, 113 * 1024);
-  stft_mel_kernel<<<grid, kWarps * 32, smem, s>>>(y, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag,
-                                                   frame_major, e_input, e_min, e_input != nullptr ? 1.0f / (e_max - e_min) : 0.f,
-                                                   n_samples);
-  SB_LAUNCH_OK();
-  return 0;
+  const float e_inv = e_input != nullptr ? 1.0f / (e_max - e_min) : 0.f;
+  using Two = StftLaunch<32, 8, 2, false>;     // 2 CTAs x 8 warps per SM
+  using Three = StftLaunch<16, 8, 3, true>;    // 3 CTAs x 8 warps per SM
+  using Wide = StftLaunch<24, 12, 2, true>;    // 2 CTAs x 12 warps per SM (prologue amortised over 24 frames)
+  const int occ = tuning(TUNE_STFT_OCC);
+  if (occ == 1 && Three::smem_bytes(n_mels) <= Three::kSmemCap)
+    return Three::run(y, B, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min,
+                      e_inv, n_samples, s);
+  if (occ == 2 && Wide::smem_bytes(n_mels) <= Wide::kSmemCap)
+    return Wide::run(y, B, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min,
+                     e_inv, n_samples, s);
+  SB_REQUIRE(Two::smem_bytes(n_mels) <= Two::kSmemCap, "stft_mel: n_mels=%d needs %zu bytes of shared memory", n_mels,
+             Two::smem_bytes(n_mels));
+  return Two::run(y, B, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min, e_inv,
+                  n_samples, s);
 }
 
 extern "C" int styler_stft_mel_fwd(const float* y, int32_t B, int32_t N, const float* mel_basis, int32_t n_mels,

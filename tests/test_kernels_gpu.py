@@ -625,3 +625,38 @@ def test_stft_mel(cuda):
     m2, e2 = ops.stft_mel(y2.to(cuda), basis.to(cuda))
     assert m2.shape == (2, 80, 345)
     assert (m2.cpu() - m_ref).abs().max() < 1e-3 and rel_err(e2, e_ref) < 1e-4
+
+
+@pytest.mark.parametrize("occ", [1, 2], ids=["three_ctas", "twelve_warps"])
+def test_stft_occupancy_shapes_bitwise(cuda, occ):
+    """The STFT kernel's higher-occupancy shapes (STFT_OCC: 16 frames x 3 CTAs per SM / 24 frames x 12 warps, magnitudes aliased onto
+    the FFT exchange buffer) run the same arithmetic per frame as the 32-frame shape: every output must be bitwise equal, on the
+    plain entry and on the extended one (ragged per-utterance lengths, frame-major mel, clamp + clip flag, energy rescaling)."""
+    from styler_b200 import _lib
+    ops = _ops()
+    g = torch.Generator().manual_seed(41)
+    basis = torch.from_numpy(stft_oracle.slaney_mel_basis(22050, 1024, 80, 0.0, 8000.0)).to(cuda)
+    y = ((torch.rand(5, 30000, generator=g) * 2 - 1) * 0.8).to(cuda)
+    ns = torch.tensor([30000, 12345, 700, 29999, 8192], dtype=torch.int64, device=cuda)
+
+    def run():
+        a = ops.stft_mel(y, basis)
+        b = ops.stft_mel_ex(y * 1.5, basis, in_scale=1.0, clamp=True, frame_major=True, energy_range=(0.1, 525.43), n_samples=ns)
+        c = ops.stft_mel_ex(y, basis, n_samples=ns)
+        torch.cuda.synchronize()
+        return list(a) + list(b) + [c[0], c[1]]
+
+    try:
+        _lib.set_tuning("STFT_OCC", 0)
+        base = run()
+        _lib.set_tuning("STFT_OCC", occ)
+        n0 = _lib.launch_count()
+        got = run()
+        assert _lib.launch_count() == n0 + 6        # band kernel + transform kernel per call
+    finally:
+        _lib.set_tuning("STFT_OCC", -1)
+    assert len(base) == len(got) == 8
+    for i, (p, q) in enumerate(zip(base, got)):
+        assert torch.isfinite(q.float()).all(), i
+        assert torch.equal(p, q), i
+    assert base[4].any()                             # the clip flag saw the scaled samples below -1
