@@ -13,7 +13,8 @@ namespace sb {
 namespace {
 
 constexpr int NFFT = 1024, HOP = 256, NBINS = 513, HALF = 512;
-constexpr int WBUF = HALF + HALF / 16;               // complex work buffer per warp, skewed: slot(i) = i + (i >> 4)
+constexpr int WBUF = HALF;                           // complex work buffer per warp, XOR-swizzled (slot() below): every 8-byte
+                                                     // access pattern of the three passes hits 16 distinct banks per half-warp
 constexpr int MAGLD = NBINS + 3;
 // Two shapes of the same arithmetic (bitwise-equal results, tests/test_kernels_gpu.py):
 //   <32, 8, 2, false>: 32 frames per CTA (one 128-byte run of every mel row), separate magnitude buffer, 107 KB of smem -> 2 CTAs
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
   float2* tw = reinterpret_cast<float2*>(stft_smem);                       // W_1024^k, k < 512
   float2* twA = tw + HALF;                                                 // W_64^k,  k < 8   (pass-2 base twiddles)
   float2* twB = twA + 8;                                                   // W_512^k, k < 64  (pass-3 base twiddles)
-  float2* wbuf = twB + 64;                                                 // [KW][WBUF]
+  float2* win = twB + 64;                                                  // periodic Hann window as pairs (w[2n], w[2n+1]), n < 512
+  float2* wbuf = win + HALF;                                               // [KW][WBUF]
   float* samp = reinterpret_cast<float*>(wbuf + KW * WBUF);            // [NSAMP]
   float* mag = samp + NSAMP;                                               // [KW][MAGLD] (absent when ALIAS_MAG)
   float* s_en = mag + (ALIAS_MAG ? 0 : KW * MAGLD);                    // [FPB]
@@ -191,6 +193,13 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
   }
   if (clipped && clip_flag != nullptr) clip_flag[b] = 1;   // one (benign, same-value) store per thread after the staging
   __syncthreads();
+  for (int n = threadIdx.x; n < HALF; n += KW * 32) {
+    // periodic Hann: 0.5 - 0.5 cos(2 pi i / 1024), cos(2 pi i / 1024) = Re W^i = -Re W^(i-512); one 8-byte table read per
+    // sample pair in pass 1 (reading the twiddle table there cost a 16-byte read + an FFMA2 per pair)
+    const float4 c = reinterpret_cast<const float4*>(tw)[n & (HALF / 2 - 1)];   // (Re W^2n, Im W^2n, Re W^(2n+1), Im W^(2n+1))
+    const float sg = n < HALF / 2 ? -0.5f : 0.5f;
+    win[n] = __ffma2_rn(make_float2(sg, sg), make_float2(c.x, c.z), make_float2(0.5f, 0.5f));
+  }
   if (threadIdx.x < 32) {   // exclusive prefix of the band widths: warp scan, 32 rows at a time (a one-thread loop stalled the CTA)
     int base = 0;
     for (int m0 = 0; m0 < n_mels; m0 += 32) {
@@ -220,24 +229,22 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* wb = wbuf + warp * WBUF;
   float* mg = ALIAS_MAG ? reinterpret_cast<float*>(wb) : mag + warp * MAGLD;   // 513 floats; wb holds 2 * WBUF
-  auto slot = [](int i) { return i + (i >> 4); };
+  // bank (8-byte units, 16 per half-warp wavefront) = low four index bits ^ (i6, i6, i5, i4): conflict-free for the pass-1 stores
+  // (i = 8 j + r), the strided loads (i = j + 64 r), the pass-2 stores (i = 64 a + 8 r + k: the additive skew i + (i >> 4) of the
+  // first version was two-way conflicted there) and the pass-3 stores / split reads (consecutive i)
+  auto slot = [](int i) { const int t = (i >> 4) & 7; return i ^ (t | ((t & 4) << 1)); };
   for (int fl = warp; fl < FPB; fl += KW) {
     if (f0 + fl >= Fb) break;                   // warp-uniform
     float2 v[2][8];
     // ---- pass 1 (Ns = 1): window, pack z[n] = x[2n] + i x[2n+1], butterfly, no twiddles
     {
       const float2* sp = reinterpret_cast<const float2*>(samp + fl * HOP);   // fl*HOP is even -> 8-byte aligned
-      const float4* tw2 = reinterpret_cast<const float4*>(tw);               // (Re W^2n, Im W^2n, Re W^(2n+1), Im W^(2n+1))
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int n = lane + 32 * u + 64 * r;
-          const float2 x = sp[n];
-          // periodic Hann: 0.5 - 0.5 cos(2 pi i / 1024), cos(2 pi i / 1024) = Re W^i = -Re W^(i-512)
-          const float4 c = tw2[n & (HALF / 2 - 1)];
-          const float sg = n < HALF / 2 ? -0.5f : 0.5f;
-          v[u][r] = __fmul2_rn(x, __ffma2_rn(make_float2(sg, sg), make_float2(c.x, c.z), make_float2(0.5f, 0.5f)));
+          v[u][r] = __fmul2_rn(sp[n], win[n]);
         }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
 
 template <int FPB, int KW, int MINB, bool ALIAS_MAG> struct StftLaunch {
   static size_t smem_bytes(int n_mels) {
-    return sizeof(float2) * (HALF + 8 + 64) + sizeof(float2) * KW * WBUF + sizeof(float) * StftShape<FPB>::NSAMP +
+    return sizeof(float2) * (2 * HALF + 8 + 64) + sizeof(float2) * KW * WBUF + sizeof(float) * StftShape<FPB>::NSAMP +
            (ALIAS_MAG ? 0 : sizeof(float) * KW * MAGLD) + sizeof(float) * FPB + sizeof(float) * kBasisCap +
            sizeof(int) * (3 * n_mels + 1) + sizeof(float) * n_mels * StftShape<FPB>::MELLD;
   }
