@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
                                                                   float* __restrict__ mel, float* __restrict__ energy,
                                                                   float in_scale, int clamp, int32_t* __restrict__ clip_flag,
                                                                   int frame_major, float* __restrict__ e_input, float e_min,
-                                                                  float e_inv_range, const int64_t* __restrict__ n_samples) {
+                                                                  float e_inv_range, const int64_t* __restrict__ n_samples,
+                                                                  int n_items) {
   constexpr int NSAMP = StftShape<FPB>::NSAMP, MELLD = StftShape<FPB>::MELLD;
   extern __shared__ __align__(16) uint8_t stft_smem[];
   float2* tw = reinterpret_cast<float2*>(stft_smem);                       // W_1024^k, k < 512
@@ -103,71 +104,11 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
   int* s_hi = s_lo + n_mels;                                               // [n_mels] one past the last bin
   int* s_off = s_hi + n_mels;                                              // [n_mels + 1] offset of the band in s_basis
   float* s_mel = reinterpret_cast<float*>(s_off + n_mels + 1);             // [n_mels][MELLD]
-  const int b = blockIdx.y, f0 = blockIdx.x * FPB;
-  const float* yb = y + static_cast<long long>(b) * N;
-  // Per-utterance length (audio/tools.py:37-55 runs every utterance alone): row b of the zero-padded batch holds Nb valid
-  // samples, is reflected around ITS OWN end and yields Fb = 1 + Nb/hop frames; frames >= Fb are written as zeros (the
-  // collation padding of dataset.py:160-166).  `N` stays the row stride and `F` the padded frame count of the outputs.
-  if (n_samples != nullptr) {
-    const long long nb = n_samples[b];
-    N = nb < N ? (nb > NFFT / 2 ? static_cast<int>(nb) : NFFT / 2 + 1) : N;
-  }
-  const int Fb = n_samples != nullptr ? min(F, 1 + N / HOP) : F;
-  if (f0 >= Fb) {   // block-uniform: this whole block of frames is padding
-    const int nf = min(FPB, F - f0);
-    for (int i = threadIdx.x; i < n_mels * nf; i += KW * 32) {
-      if (frame_major) mel[(static_cast<long long>(b) * F + f0) * n_mels + i] = 0.f;
-      else mel[(static_cast<long long>(b) * n_mels + i / nf) * F + f0 + i % nf] = 0.f;
-    }
-    if (threadIdx.x < nf) {
-      energy[static_cast<long long>(b) * F + f0 + threadIdx.x] = 0.f;
-      if (e_input != nullptr) e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = 0.f;
-    }
-    return;
-  }
-  bool clipped = false;
-  auto scale_clamp = [&](float x) {
-    x *= in_scale;
-    if (clamp) {   // get_mel_from_wav(norm=False), audio/tools.py:44-49: clamp to [-1,1]; the flag only sees the NEGATIVE side
-      clipped |= x < -1.f;
-      x = fminf(fmaxf(x, -1.f), 1.f);
-    }
-    return x;
-  };
-  // Sample window of the block.  Interior blocks (no reflection, 16-byte aligned start: all but the first / last two blocks of an
-  // utterance) issue ALL of their loads as float4 here, before the twiddle / band set-up below, and store them after it: one
-  // memory round trip per CTA (the scalar loop -- four loads in flight, NSAMP / 1024 round trips -- was 10-13 % of the kernel's
-  // warp-state samples on long-scoreboard waits, profiles/ncu_stft_r2l_packed.md).
-  constexpr int NV = NSAMP / 4, PER = (NV + KW * 32 - 1) / (KW * 32);
-  const int first = f0 * HOP - NFFT / 2;
-  const bool interior = first >= 0 && first + NSAMP <= N && (reinterpret_cast<uintptr_t>(yb + (first >= 0 ? first : 0)) & 15u) == 0;
-  float4 v4[PER];
-  if (interior) {
-    const float4* src4 = reinterpret_cast<const float4*>(yb + first);
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-      const int idx = u * KW * 32 + threadIdx.x;
-      if (idx < NV) v4[u] = __ldg(src4 + idx);
-    }
-  } else {
-    for (int i0 = 0; i0 < NSAMP; i0 += 4 * KW * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
-      float v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {                         // four independent loads in flight before anything is stored
-        const int i = i0 + u * KW * 32 + threadIdx.x;
-        int src = first + i;
-        if (src < 0) src = -src;
-        if (src >= N) src = 2 * (N - 1) - src;
-        v[u] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * KW * 32 + threadIdx.x;
-        const float x = scale_clamp(v[u]);
-        if (i < NSAMP) samp[i] = x;
-      }
-    }
-  }
+  // ---- once per CTA: twiddles, window, band tables, basis bands.  The CTA is PERSISTENT: it walks work items (utterance,
+  // block of FPB frames) item = blockIdx.x + i * gridDim.x.  With one item per CTA this set-up (512 sincospif, the band scan, ten
+  // dependent global reads per warp for the basis bands, three block barriers) was 21 % of the kernel's instructions and 47 %
+  // of its warp-state samples (profiles/ncu_stft_r3e.md).
+  const int N_row = N;
   for (int k = threadIdx.x; k < HALF; k += KW * 32) {
     float sn, cs;
     sincospif(-static_cast<float>(k) / 512.0f, &sn, &cs);
@@ -180,18 +121,6 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
     (threadIdx.x < 8 ? twA : twB)[k] = make_float2(cs, sn);
   }
   for (int m = threadIdx.x; m < n_mels; m += KW * 32) { s_lo[m] = band[2 * m]; s_hi[m] = band[2 * m + 1]; }
-  if (interior) {
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-      const int idx = u * KW * 32 + threadIdx.x;
-      if (idx < NV) {
-        float4 x = v4[u];
-        x.x = scale_clamp(x.x); x.y = scale_clamp(x.y); x.z = scale_clamp(x.z); x.w = scale_clamp(x.w);
-        reinterpret_cast<float4*>(samp)[idx] = x;
-      }
-    }
-  }
-  if (clipped && clip_flag != nullptr) clip_flag[b] = 1;   // one (benign, same-value) store per thread after the staging
   __syncthreads();
   for (int n = threadIdx.x; n < HALF; n += KW * 32) {
     // periodic Hann: 0.5 - 0.5 cos(2 pi i / 1024), cos(2 pi i / 1024) = Re W^i = -Re W^(i-512); one 8-byte table read per
@@ -200,7 +129,7 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
     const float sg = n < HALF / 2 ? -0.5f : 0.5f;
     win[n] = __ffma2_rn(make_float2(sg, sg), make_float2(c.x, c.z), make_float2(0.5f, 0.5f));
   }
-  if (threadIdx.x < 32) {   // exclusive prefix of the band widths: warp scan, 32 rows at a time (a one-thread loop stalled the CTA)
+  if (threadIdx.x < 32) {   // exclusive prefix of the band widths: warp scan, 32 rows at a time
     int base = 0;
     for (int m0 = 0; m0 < n_mels; m0 += 32) {
       const int m = m0 + threadIdx.x;
@@ -224,9 +153,90 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
       for (int i = threadIdx.x & 31; i < w; i += 32) s_basis[s_off[m] + i] = basis[static_cast<long long>(m) * NBINS + lo + i];
     }
   }
-  __syncthreads();
+  // (the first item's post-staging barrier also publishes the tables above)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blocks_per_utt = (F + FPB - 1) / FPB;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int b = item / blocks_per_utt, f0 = (item - b * blocks_per_utt) * FPB;
+  const float* yb = y + static_cast<long long>(b) * N_row;
+  // Per-utterance length (audio/tools.py:37-55 runs every utterance alone): row b of the zero-padded batch holds Nb valid
+  // samples, is reflected around ITS OWN end and yields Fb = 1 + Nb/hop frames; frames >= Fb are written as zeros (the
+  // collation padding of dataset.py:160-166).  `N_row` stays the row stride and `F` the padded frame count of the outputs.
+  N = N_row;
+  if (n_samples != nullptr) {
+    const long long nb = n_samples[b];
+    N = nb < N ? (nb > NFFT / 2 ? static_cast<int>(nb) : NFFT / 2 + 1) : N;
+  }
+  const int Fb = n_samples != nullptr ? min(F, 1 + N / HOP) : F;
+  if (f0 >= Fb) {   // block-uniform: this whole block of frames is padding (no barrier is skipped by part of the CTA)
+    const int nf = min(FPB, F - f0);
+    for (int i = threadIdx.x; i < n_mels * nf; i += KW * 32) {
+      if (frame_major) mel[(static_cast<long long>(b) * F + f0) * n_mels + i] = 0.f;
+      else mel[(static_cast<long long>(b) * n_mels + i / nf) * F + f0 + i % nf] = 0.f;
+    }
+    if (threadIdx.x < nf) {
+      energy[static_cast<long long>(b) * F + f0 + threadIdx.x] = 0.f;
+      if (e_input != nullptr) e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = 0.f;
+    }
+    continue;
+  }
+  bool clipped = false;
+  auto scale_clamp = [&](float x) {
+    x *= in_scale;
+    if (clamp) {   // get_mel_from_wav(norm=False), audio/tools.py:44-49: clamp to [-1,1]; the flag only sees the NEGATIVE side
+      clipped |= x < -1.f;
+      x = fminf(fmaxf(x, -1.f), 1.f);
+    }
+    return x;
+  };
+  // Sample window of the block.  Interior blocks (no reflection, 16-byte aligned start: all but the first / last two blocks of an
+  // utterance) issue ALL of their loads as float4 before the first store: one memory round trip per item (the scalar loop --
+  // four loads in flight, NSAMP / 1024 round trips -- was 10-13 % of the kernel's warp-state samples on long-scoreboard waits,
+  // profiles/ncu_stft_r2l_packed.md).  `samp` is free here: every warp has passed the barrier behind the previous item's frames.
+  constexpr int NV = NSAMP / 4, PER = (NV + KW * 32 - 1) / (KW * 32);
+  const int first = f0 * HOP - NFFT / 2;
+  const bool interior = first >= 0 && first + NSAMP <= N && (reinterpret_cast<uintptr_t>(yb + (first >= 0 ? first : 0)) & 15u) == 0;
+  if (interior) {
+    float4 v4[PER];
+    const float4* src4 = reinterpret_cast<const float4*>(yb + first);
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * KW * 32 + threadIdx.x;
+      if (idx < NV) v4[u] = __ldg(src4 + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = u * KW * 32 + threadIdx.x;
+      if (idx < NV) {
+        float4 x = v4[u];
+        x.x = scale_clamp(x.x); x.y = scale_clamp(x.y); x.z = scale_clamp(x.z); x.w = scale_clamp(x.w);
+        reinterpret_cast<float4*>(samp)[idx] = x;
+      }
+    }
+  } else {
+    for (int i0 = 0; i0 < NSAMP; i0 += 4 * KW * 32) {   // reflect-padded sample window (F.pad mode='reflect', stft.py:58-62)
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                         // four independent loads in flight before anything is stored
+        const int i = i0 + u * KW * 32 + threadIdx.x;
+        int src = first + i;
+        if (src < 0) src = -src;
+        if (src >= N) src = 2 * (N - 1) - src;
+        v[u] = (i < NSAMP && src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * KW * 32 + threadIdx.x;
+        const float x = scale_clamp(v[u]);
+        if (i < NSAMP) samp[i] = x;
+      }
+    }
+  }
+  if (clipped && clip_flag != nullptr) clip_flag[b] = 1;   // one (benign, same-value) store per thread after the staging
+  __syncthreads();   // samples staged (first item: tables too); also orders the previous item's output stores (reads of s_mel /
+                     // s_en) before this item's frames overwrite them
+
   float2* wb = wbuf + warp * WBUF;
   float* mg = ALIAS_MAG ? reinterpret_cast<float*>(wb) : mag + warp * MAGLD;   // 513 floats; wb holds 2 * WBUF
   // bank (8-byte units, 16 per half-warp wavefront) = low four index bits ^ (i6, i6, i5, i4): conflict-free for the pass-1 stores
@@ -353,6 +363,7 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
     if (e_input != nullptr)   // energy_rescaling, utils.py:412-416
       e_input[static_cast<long long>(b) * F + f0 + threadIdx.x] = ok ? fminf(fmaxf((e - e_min) * e_inv_range, 0.f), 1.f) : 0.f;
   }
+  }   // item loop
 }
 
 
@@ -368,8 +379,12 @@ template <int FPB, int KW, int MINB, bool ALIAS_MAG> struct StftLaunch {
                  float e_inv, const int64_t* n_samples, cudaStream_t s) {
     static DeviceFlags attr_set;
     SB_OPT_IN_SMEM(attr_set, (stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG>), kSmemCap);
-    stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG><<<dim3(ceil_div(F, FPB), B), KW * 32, smem_bytes(n_mels), s>>>(
-        y, N, F, basis, band, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min, e_inv, n_samples);
+    const long long items = static_cast<long long>(ceil_div(F, FPB)) * B;
+    SB_REQUIRE(items < (1ll << 31), "stft_mel: too many frame blocks (%lld)", items);
+    const int grid = static_cast<int>(items < static_cast<long long>(MINB) * num_sms() ? items : static_cast<long long>(MINB) * num_sms());
+    stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG><<<grid, KW * 32, smem_bytes(n_mels), s>>>(
+        y, N, F, basis, band, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min, e_inv, n_samples,
+        static_cast<int>(items));
     SB_LAUNCH_OK();
     return 0;
   }
