@@ -62,11 +62,12 @@ struct TuneDef { const char* name; int dflt, lo, hi; };
 // by an FMA-pipe polynomial instead of MUFU.EX2 (0 | 2 | 3 | 4; 16-bit operands);  LSTM_MMA: BiLSTM recurrence on mma.sync,
 // sixteen utterances per CTA (16-bit activations, batches >= 8);  STFT_OCC: STFT shape with three CTAs per SM (16 frames per CTA,
 // magnitudes aliased onto the FFT exchange buffer: 1) or two CTAs of twelve warps (24 frames per CTA: 2) instead of two CTAs of
-// eight warps (0); bitwise-equal results
+// eight warps (0); 3 = shape 1 with the samples read straight from global memory by the frame's own warp (no staged block
+// window, one barrier per item); bitwise-equal results
 const TuneDef kTune[TUNE_COUNT] = {{"TC_2CTA", 1, 0, 2}, {"TC_PERSIST", 1, 0, 2}, {"CONV_WIN", 1, 0, 1}, {"TC_BN", 0, 0, 256},
                                    {"TC_SMEM_KB", 113, 64, 220}, {"PDL", 0, 0, 1}, {"ATTN_PERSIST", 1, 0, 1}, {"TC_WIDE", 1, 0, 1},
                                    {"LSTM_MULTI", 0, 0, 1}, {"ATTN_POLY", 2, 0, 4},
-                                   {"LSTM_MMA", 1, 0, 1}, {"STFT_OCC", 1, 0, 2}};
+                                   {"LSTM_MMA", 1, 0, 1}, {"STFT_OCC", 3, 0, 3}};
 std::atomic<int> g_tune[TUNE_COUNT];          // 0 = not resolved yet, else value + 1
 }  // namespace
 

@@ -80,7 +80,7 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 // One warp = one frame: 512-point complex Stockham FFT as three radix-8 passes (Ns = 1, 8, 64), each lane owning two
 // 8-point butterflies per pass held in registers; the passes exchange data through a per-warp smem buffer, so the only
 // synchronisation inside the transform is __syncwarp().
-template <int FPB, int KW, int MINB, bool ALIAS_MAG>
+template <int FPB, int KW, int MINB, bool ALIAS_MAG, bool DIRECT>
 __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __restrict__ y, int N, int F,
                                                                   const float* __restrict__ basis,
                                                                   const int32_t* __restrict__ band, int n_mels,
@@ -96,14 +96,14 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
   float2* twB = twA + 8;                                                   // W_512^k, k < 64  (pass-3 base twiddles)
   float2* win = twB + 64;                                                  // periodic Hann window as pairs (w[2n], w[2n+1]), n < 512
   float2* wbuf = win + HALF;                                               // [KW][WBUF]
-  float* samp = reinterpret_cast<float*>(wbuf + KW * WBUF);            // [NSAMP]
-  float* mag = samp + NSAMP;                                               // [KW][MAGLD] (absent when ALIAS_MAG)
-  float* s_en = mag + (ALIAS_MAG ? 0 : KW * MAGLD);                    // [FPB]
-  float* s_basis = s_en + FPB;                                             // [kBasisCap] bands of the mel basis, back to back
+  float* samp = reinterpret_cast<float*>(wbuf + KW * WBUF);                // [NSAMP] (absent when DIRECT)
+  float* mag = samp + (DIRECT ? 0 : NSAMP);                                // [KW][MAGLD] (absent when ALIAS_MAG)
+  float* s_en0 = mag + (ALIAS_MAG ? 0 : KW * MAGLD);                       // [FPB], two buffers when DIRECT
+  float* s_basis = s_en0 + (DIRECT ? 2 : 1) * FPB;                         // [kBasisCap] bands of the mel basis, back to back
   int* s_lo = reinterpret_cast<int*>(s_basis + kBasisCap);                 // [n_mels] first bin of the band
   int* s_hi = s_lo + n_mels;                                               // [n_mels] one past the last bin
   int* s_off = s_hi + n_mels;                                              // [n_mels + 1] offset of the band in s_basis
-  float* s_mel = reinterpret_cast<float*>(s_off + n_mels + 1);             // [n_mels][MELLD]
+  float* s_mel0 = reinterpret_cast<float*>(s_off + n_mels + 1);            // [n_mels][MELLD], two buffers when DIRECT
   // ---- once per CTA: twiddles, window, band tables, basis bands.  The CTA is PERSISTENT: it walks work items (utterance,
   // block of FPB frames) item = blockIdx.x + i * gridDim.x.  With one item per CTA this set-up (512 sincospif, the band scan, ten
   // dependent global reads per warp for the basis bands, three block barriers) was 21 % of the kernel's instructions and 47 %
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
       for (int i = threadIdx.x & 31; i < w; i += 32) s_basis[s_off[m] + i] = basis[static_cast<long long>(m) * NBINS + lo + i];
     }
   }
-  // (the first item's post-staging barrier also publishes the tables above)
+  if (DIRECT) __syncthreads();   // (staged form: the first item's post-staging barrier publishes the tables above)
+  int parity = 0;                // DIRECT: which output tile (s_mel / s_en) this item fills
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blocks_per_utt = (F + FPB - 1) / FPB;
@@ -181,6 +182,8 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
     }
     continue;
   }
+  float* s_mel = s_mel0 + (DIRECT ? parity * n_mels * MELLD : 0);
+  float* s_en = s_en0 + (DIRECT ? parity * FPB : 0);
   bool clipped = false;
   auto scale_clamp = [&](float x) {
     x *= in_scale;
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
   constexpr int NV = NSAMP / 4, PER = (NV + KW * 32 - 1) / (KW * 32);
   const int first = f0 * HOP - NFFT / 2;
   const bool interior = first >= 0 && first + NSAMP <= N && (reinterpret_cast<uintptr_t>(yb + (first >= 0 ? first : 0)) & 15u) == 0;
+  if constexpr (!DIRECT) {
   if (interior) {
     float4 v4[PER];
     const float4* src4 = reinterpret_cast<const float4*>(yb + first);
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
   if (clipped && clip_flag != nullptr) clip_flag[b] = 1;   // one (benign, same-value) store per thread after the staging
   __syncthreads();   // samples staged (first item: tables too); also orders the previous item's output stores (reads of s_mel /
                      // s_en) before this item's frames overwrite them
+  }  // !DIRECT
 
   float2* wb = wbuf + warp * WBUF;
   float* mg = ALIAS_MAG ? reinterpret_cast<float*>(wb) : mag + warp * MAGLD;   // 513 floats; wb holds 2 * WBUF
@@ -248,14 +253,55 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
     float2 v[2][8];
     // ---- pass 1 (Ns = 1): window, pack z[n] = x[2n] + i x[2n+1], butterfly, no twiddles
     {
-      const float2* sp = reinterpret_cast<const float2*>(samp + fl * HOP);   // fl*HOP is even -> 8-byte aligned
+      if constexpr (DIRECT) {
+        // DIRECT: the frame's 1024 samples come straight from global memory (16 coalesced 8-byte loads per lane, all in flight
+        // together; the 4x overlap between neighbouring frames is served by L1 / L2): no staging pass, no block barrier before
+        // the frames, and the load latency stalls one warp instead of the CTA.  Same arithmetic as the staged form
+        // (x * in_scale, clamp, * window), so the results are bitwise equal.
+        const int start = (f0 + fl) * HOP - NFFT / 2;
+        const bool whole = start >= 0 && start + NFFT <= N && (reinterpret_cast<uintptr_t>(yb + (start >= 0 ? start : 0)) & 7u) == 0;
+        if (whole) {
+          const float2* gp = reinterpret_cast<const float2*>(yb + start);
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int n = lane + 32 * u + 64 * r;
-          v[u][r] = __fmul2_rn(sp[n], win[n]);
+            for (int r = 0; r < 8; ++r) v[u][r] = __ldg(gp + lane + 32 * u + 64 * r);
+        } else {                                 // frames that touch either end of the utterance: reflect (stft.py:58-62)
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              float xs[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                int src = start + 2 * (lane + 32 * u + 64 * r) + e;
+                if (src < 0) src = -src;
+                if (src >= N) src = 2 * (N - 1) - src;
+                xs[e] = (src >= 0 && src < N) ? __ldg(yb + src) : 0.f;
+              }
+              v[u][r] = make_float2(xs[0], xs[1]);
+            }
         }
+        if (in_scale != 1.0f || clamp) {         // block-uniform; x * 1.0f is exact, so skipping it changes nothing
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { v[u][r].x = scale_clamp(v[u][r].x); v[u][r].y = scale_clamp(v[u][r].y); }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int r = 0; r < 8; ++r) v[u][r] = __fmul2_rn(v[u][r], win[lane + 32 * u + 64 * r]);
+      } else {
+        const float2* sp = reinterpret_cast<const float2*>(samp + fl * HOP);   // fl*HOP is even -> 8-byte aligned
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int n = lane + 32 * u + 64 * r;
+            v[u][r] = __fmul2_rn(sp[n], win[n]);
+          }
+      }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         dft8(v[u]);
@@ -341,7 +387,9 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
     }
     __syncwarp();                               // mg / wb are reused by this warp's next frame
   }
-  __syncthreads();
+  if (DIRECT && clipped && clip_flag != nullptr) clip_flag[b] = 1;
+  __syncthreads();   // DIRECT: the only barrier of an item.  The tile read below is not written again before the NEXT item's
+  parity ^= 1;       // barrier (the next item fills the other tile), by which time every warp has finished these stores
   // coalesced stores: FPB consecutive frames of one mel row are contiguous in mel[b][m][:]
   const int nf = min(FPB, F - f0);
   const int nv = min(FPB, Fb - f0);            // valid frames of this block; [nv, nf) is per-utterance padding -> zeros
@@ -367,22 +415,22 @@ __global__ void __launch_bounds__(KW * 32, MINB) stft_mel_kernel(const float* __
 }
 
 
-template <int FPB, int KW, int MINB, bool ALIAS_MAG> struct StftLaunch {
+template <int FPB, int KW, int MINB, bool ALIAS_MAG, bool DIRECT = false> struct StftLaunch {
   static size_t smem_bytes(int n_mels) {
-    return sizeof(float2) * (2 * HALF + 8 + 64) + sizeof(float2) * KW * WBUF + sizeof(float) * StftShape<FPB>::NSAMP +
-           (ALIAS_MAG ? 0 : sizeof(float) * KW * MAGLD) + sizeof(float) * FPB + sizeof(float) * kBasisCap +
-           sizeof(int) * (3 * n_mels + 1) + sizeof(float) * n_mels * StftShape<FPB>::MELLD;
+    return sizeof(float2) * (2 * HALF + 8 + 64) + sizeof(float2) * KW * WBUF + (DIRECT ? 0 : sizeof(float) * StftShape<FPB>::NSAMP) +
+           (ALIAS_MAG ? 0 : sizeof(float) * KW * MAGLD) + (DIRECT ? 2 : 1) * sizeof(float) * FPB + sizeof(float) * kBasisCap +
+           sizeof(int) * (3 * n_mels + 1) + (DIRECT ? 2 : 1) * sizeof(float) * n_mels * StftShape<FPB>::MELLD;
   }
   static constexpr size_t kSmemCap = (228 * 1024 - MINB * 1024) / MINB / 1024 * 1024;   // MINB CTAs per SM, 1 KB reserved each
   static int run(const float* y, int B, int N, int F, const float* basis, const int32_t* band, int n_mels, float* mel,
                  float* energy, float in_scale, int clamp, int32_t* clip_flag, int frame_major, float* e_input, float e_min,
                  float e_inv, const int64_t* n_samples, cudaStream_t s) {
     static DeviceFlags attr_set;
-    SB_OPT_IN_SMEM(attr_set, (stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG>), kSmemCap);
+    SB_OPT_IN_SMEM(attr_set, (stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG, DIRECT>), kSmemCap);
     const long long items = static_cast<long long>(ceil_div(F, FPB)) * B;
     SB_REQUIRE(items < (1ll << 31), "stft_mel: too many frame blocks (%lld)", items);
     const int grid = static_cast<int>(items < static_cast<long long>(MINB) * num_sms() ? items : static_cast<long long>(MINB) * num_sms());
-    stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG><<<grid, KW * 32, smem_bytes(n_mels), s>>>(
+    stft_mel_kernel<FPB, KW, MINB, ALIAS_MAG, DIRECT><<<grid, KW * 32, smem_bytes(n_mels), s>>>(
         y, N, F, basis, band, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min, e_inv, n_samples,
         static_cast<int>(items));
     SB_LAUNCH_OK();
@@ -410,7 +458,18 @@ extern "C" int styler_stft_mel_ex_fwd(const float* y, int32_t B, int32_t N, cons
   using Two = StftLaunch<32, 8, 2, false>;     // 2 CTAs x 8 warps per SM
   using Three = StftLaunch<16, 8, 3, true>;    // 3 CTAs x 8 warps per SM
   using Wide = StftLaunch<24, 12, 2, true>;    // 2 CTAs x 12 warps per SM (prologue amortised over 24 frames)
+  using Direct = StftLaunch<16, 8, 3, true, true>;   // 3 CTAs x 8 warps per SM, samples read from global by the frame's own warp
   const int occ = tuning(TUNE_STFT_OCC);
+  // (rows that are not 8-byte aligned -- odd N -- would take the direct form's scalar edge path for every frame: they keep the
+  // staged form, whose block window is staged once either way)
+  const bool rows_aligned = (N % 2) == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0;
+  if (occ == 3 && !rows_aligned) {
+    if (Three::smem_bytes(n_mels) <= Three::kSmemCap)
+      return Three::run(y, B, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min,
+                        e_inv, n_samples, s);
+  } else if (occ == 3 && Direct::smem_bytes(n_mels) <= Direct::kSmemCap)
+    return Direct::run(y, B, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min,
+                       e_inv, n_samples, s);
   if (occ == 1 && Three::smem_bytes(n_mels) <= Three::kSmemCap)
     return Three::run(y, B, N, F, mel_basis, band_ws, n_mels, mel, energy, in_scale, clamp, clip_flag, frame_major, e_input, e_min,
                       e_inv, n_samples, s);

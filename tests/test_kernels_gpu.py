@@ -627,10 +627,11 @@ def test_stft_mel(cuda):
     assert (m2.cpu() - m_ref).abs().max() < 1e-3 and rel_err(e2, e_ref) < 1e-4
 
 
-@pytest.mark.parametrize("occ", [1, 2], ids=["three_ctas", "twelve_warps"])
+@pytest.mark.parametrize("occ", [1, 2, 3], ids=["three_ctas", "twelve_warps", "direct_loads"])
 def test_stft_occupancy_shapes_bitwise(cuda, occ):
     """The STFT kernel's higher-occupancy shapes (STFT_OCC: 16 frames x 3 CTAs per SM / 24 frames x 12 warps, magnitudes aliased onto
-    the FFT exchange buffer) run the same arithmetic per frame as the 32-frame shape: every output must be bitwise equal, on the
+    the FFT exchange buffer; 3: samples read from global memory by the frame's own warp instead of a staged block window) run the
+    same arithmetic per frame as the 32-frame shape: every output must be bitwise equal, on the
     plain entry and on the extended one (ragged per-utterance lengths, frame-major mel, clamp + clip flag, energy rescaling)."""
     from styler_b200 import _lib
     ops = _ops()

@@ -18,7 +18,7 @@ y = ((torch.rand(4, 20000, generator=g) * 2 - 1) * 0.9).to(dev)
 ns = torch.tensor([20000, 9000, 600, 19999], dtype=torch.int64, device=dev)
 big = ((torch.rand(48, 44100, generator=g) * 2 - 1) * 0.5).to(dev)      # 48 x 11 blocks of 16 frames > 3 x 148 CTAs: item loop
 ref = None
-for occ in (0, 1, 2):
+for occ in (0, 1, 2, 3):
     _lib.set_tuning("STFT_OCC", occ)
     a = ops.stft_mel(y, basis)
     b = ops.stft_mel_ex(y * 1.2, basis, clamp=True, frame_major=True, energy_range=(0.1, 525.43), n_samples=ns)
