@@ -1,12 +1,16 @@
 // TacotronSTFT.mel_spectrogram (audio/stft.py:51-79,141-160; audio_processing.py:80-86 of the reference).
 // The reference evaluates a dense 1026x1024 DFT as a strided Conv1d (2.1 MFLOP/frame) and bounces through
-// the host; here one CTA handles 32 consecutive frames of one utterance, one frame per warp at a time:
-//   stage the 31*256+1024 reflect-padded samples in smem once (the 4x frame overlap is served from smem),
-//   periodic-Hann window, 1024-point real FFT as a 512-point complex Stockham FFT (three radix-8 passes, 16 points per
-//   lane in registers, warp-private smem exchange) + split post-pass, magnitude for the 513 bins,
-//   energy = ||mag||_2, mel = log(max(basis @ mag, 1e-5)) over the non-zero band of each filter row, staged in smem
-//   and stored as 128-byte runs.
-// Bounding roofline: HBM (464,580 algorithmic bytes per 4 s utterance); the FFT stage is ALU/smem work.
+// the host.  Here persistent CTAs (three per SM) walk work items = 16 consecutive frames of one utterance, one frame per
+// warp at a time:
+//   the frame's 1024 reflect-padded samples go straight from global memory into the registers of pass 1 (16 coalesced
+//   8-byte loads per lane; the 4x overlap between frames is served by L1/L2) -- or, in the staged shapes, from a block
+//   window staged once in smem --, periodic-Hann window from an smem table, 1024-point real FFT as a 512-point complex
+//   Stockham FFT (three radix-8 passes, 16 points per lane in registers, warp-private XOR-swizzled smem exchange) + split
+//   post-pass, magnitude for the 513 bins, energy = ||mag||_2, mel = log(max(basis @ mag, 1e-5)) over the non-zero band of
+//   each filter row (bands cached in smem once per CTA), results staged in a double-buffered smem tile and stored as runs
+//   of 16 frames per mel row.
+// Bounding roofline: HBM by contract (464,580 algorithmic bytes per 4 s utterance); in practice the kernel is latency /
+// issue bound (1.7 k warp-instructions per frame, issue slots 61 % busy at 6 warps per scheduler): profiles/ncu_stft_r2_final.md.
 #include "common.cuh"
 
 namespace sb {
@@ -16,12 +20,13 @@ constexpr int NFFT = 1024, HOP = 256, NBINS = 513, HALF = 512;
 constexpr int WBUF = HALF;                           // complex work buffer per warp, XOR-swizzled (slot() below): every 8-byte
                                                      // access pattern of the three passes hits 16 distinct banks per half-warp
 constexpr int MAGLD = NBINS + 3;
-// Two shapes of the same arithmetic (bitwise-equal results, tests/test_kernels_gpu.py):
-//   <32, 8, 2, false>: 32 frames per CTA (one 128-byte run of every mel row), separate magnitude buffer, 107 KB of smem -> 2 CTAs
-//                   (16 warps) per SM, 116 registers;
-//   <16, 8, 3, true>:  16 frames per CTA, the magnitudes overwrite the warp's FFT exchange buffer (the split pass keeps its 18
-//                   results in registers across one __syncwarp), 70 KB of smem and <= 85 registers -> 3 CTAs (24 warps) per SM.
-//                   The kernel is latency-bound (issue slots 48 % busy at 4 warps per scheduler): the extra warps are the point.
+// Shapes of the same arithmetic (bitwise-equal results, tests/test_kernels_gpu.py; STFT_OCC selects):
+//   0 <32, 8, 2, staged>: 32 frames per item, separate magnitude buffer, 109 KB of smem -> 2 CTAs (16 warps) per SM, 126 registers;
+//   1 <16, 8, 3, staged>: 16 frames per item, the magnitudes overwrite the warp's FFT exchange buffer (the split pass keeps its 18
+//                         results in registers across one __syncwarp), 74 KB of smem and <= 85 registers -> 3 CTAs (24 warps) per SM;
+//   2 <24, 12, 2, staged>: 24 frames per item, two CTAs of twelve warps;
+//   3 <16, 8, 3, direct>: shape 1 without the staged block window (58 KB): every warp reads its frame from global memory itself.
+// Measured at configs[3] (256 x 4 s): 0.251 / 0.241 / 0.241 / 0.226 ms.  The kernel is latency-bound: the extra warps are the point.
 template <int FPB> struct StftShape {
   static constexpr int NSAMP = (FPB - 1) * HOP + NFFT;
   static constexpr int MELLD = FPB + 1;
