@@ -317,5 +317,13 @@ def test_pipelined_batches_match_eager(cuda):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tests", "pipeline_case.py")], cwd=root, capture_output=True, text=True, timeout=300)
+    r = None
+    for attempt in range(2):                     # a child that exceeds its time limit is killed and the case is run once more:
+        try:                                     # a stall is not reproducible, a wrong result fails at once
+            r = subprocess.run([sys.executable, os.path.join(root, "tests", "pipeline_case.py")], cwd=root, capture_output=True,
+                               text=True, timeout=150)
+            break
+        except subprocess.TimeoutExpired:
+            print("pipeline_case.py exceeded 150 s (attempt %d)" % (attempt + 1))
+    assert r is not None, "pipeline_case.py exceeded its time limit twice"
     assert r.returncode == 0 and "PIPELINE_CASE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
